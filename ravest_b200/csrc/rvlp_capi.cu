@@ -1,0 +1,420 @@
+// rvlp_capi.cu — C ABI (include/ravest_b200.h) over the kernels.  No torch, no C++ types
+// across the boundary; errors are integer codes + a thread-local message.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rvlp_gp.cuh"
+#include "rvlp_kernels.cuh"
+
+using namespace rvlp;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return fail(RVLP_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                  __LINE__);                                                                   \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int grid_for(int device, const void* kernel, int smem_bytes, int64_t want_blocks, int* grid) {
+  int sms = 0, per_sm = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem_bytes));
+  if (per_sm < 1) return fail(RVLP_EUNSUPPORTED, "kernel does not fit on an SM (smem %d B)", smem_bytes);
+  int64_t g = (int64_t)sms * per_sm;      // one full wave of resident CTAs, persistent loop inside
+  if (want_blocks < g) g = want_blocks;
+  if (g < 1) g = 1;
+  *grid = (int)g;
+  return RVLP_OK;
+}
+
+int simple_grid(int64_t n) {
+  int64_t g = (n + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+struct rvlp_ctx {
+  int device = 0;
+  DevProblem P{};
+  void* d_src_col = nullptr;
+  void* d_src_const = nullptr;
+  void* d_priors = nullptr;
+  void* d_epochs = nullptr;
+  int smem_main = 0, smem_gp = 0;
+  int max_smem = 0;
+  // host-buffer path
+  double* h_theta = nullptr;
+  double* h_out = nullptr;
+  double* d_theta = nullptr;
+  double* d_out = nullptr;
+  int64_t cap_samples = 0;
+  cudaStream_t stream = nullptr;
+};
+
+extern "C" {
+
+int rvlp_abi_version(void) { return RVLP_ABI_VERSION; }
+const char* rvlp_last_error(void) { return g_err.c_str(); }
+int64_t rvlp_launch_count(void) { return g_launches.load(); }
+
+int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, const double* velerr,
+                    const int32_t* inst_idx, int64_t n_epochs, int device, rvlp_ctx** out) {
+  if (!d || !out) return fail(RVLP_EINVAL, "null descriptor / out pointer");
+  if (d->abi_version != RVLP_ABI_VERSION)
+    return fail(RVLP_EINVAL, "descriptor ABI version %d != library %d", d->abi_version, RVLP_ABI_VERSION);
+  if (d->n_planets < 0 || d->n_inst < 1 || d->ndim < 0 || d->n_priors < 0)
+    return fail(RVLP_EINVAL, "bad descriptor sizes");
+  if (d->parameterisation < 0 || d->parameterisation > 3) return fail(RVLP_EINVAL, "bad parameterisation id");
+  if (d->n_hyper != 0 && d->n_hyper != 4) return fail(RVLP_EINVAL, "n_hyper must be 0 or 4");
+  if (n_epochs < 1 || n_epochs > (1 << 24)) return fail(RVLP_EINVAL, "bad epoch count %lld", (long long)n_epochs);
+  const int n_model = 5 * d->n_planets + 2 + 2 * d->n_inst;
+  const int n_src = n_model + d->n_hyper;
+  for (int i = 0; i < n_src; ++i)
+    if (d->src_col[i] >= d->ndim) return fail(RVLP_EINVAL, "src_col[%d] = %d out of range", i, d->src_col[i]);
+  for (int i = 0; i < d->n_priors; ++i) {
+    const rvlp_prior& p = d->priors[i];
+    if (p.kind < 0 || p.kind > RVLP_PRIOR_BETA) return fail(RVLP_EINVAL, "prior %d: bad kind", i);
+    if (p.target < 0 || p.target > RVLP_TARGET_TP) return fail(RVLP_EINVAL, "prior %d: bad target", i);
+    if (p.target == RVLP_TARGET_COLUMN ? (p.index < 0 || p.index >= d->ndim)
+                                       : (p.index < 0 || p.index >= d->n_planets))
+      return fail(RVLP_EINVAL, "prior %d: index out of range", i);
+  }
+  for (int64_t i = 0; i < n_epochs; ++i)
+    if (inst_idx[i] < 0 || inst_idx[i] >= d->n_inst) return fail(RVLP_EINVAL, "inst_idx[%lld] out of range", (long long)i);
+
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(RVLP_EINVAL, "device %d not present (%d visible)", device, ndev);
+  DeviceGuard guard(device);
+
+  rvlp_ctx* c = new rvlp_ctx();
+  c->device = device;
+  DevProblem& P = c->P;
+  P.n_planets = d->n_planets; P.par = d->parameterisation; P.n_inst = d->n_inst; P.ndim = d->ndim;
+  P.n_priors = d->n_priors; P.n_hyper = d->n_hyper; P.n_model = n_model; P.n_epochs = (int)n_epochs;
+  P.n_pad = (int)((n_epochs + 63) / 64 * 64);
+  P.t0 = d->t0; P.jacobian = d->jacobian; P.renorm = d->renorm;
+
+  // packed, padded epoch block: [t | vel | velerr^2] doubles + int32 instrument ids
+  std::vector<unsigned char> blk((size_t)P.n_pad * 28);
+  double* ht = reinterpret_cast<double*>(blk.data());
+  double* hv = ht + P.n_pad;
+  double* he = hv + P.n_pad;
+  int32_t* hi = reinterpret_cast<int32_t*>(he + P.n_pad);
+  for (int i = 0; i < P.n_pad; ++i) {
+    const bool in = i < n_epochs;
+    ht[i] = in ? time[i] : time[n_epochs - 1];
+    hv[i] = in ? vel[i] : 0.0;
+    he[i] = in ? velerr[i] * velerr[i] : 1.0;                // fit.py:3598
+    hi[i] = in ? inst_idx[i] : 0;
+  }
+#define CTX_TRY(expr)                                                                            \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      int rc = fail(RVLP_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));                 \
+      rvlp_ctx_destroy(c);                                                                       \
+      return rc;                                                                                 \
+    }                                                                                            \
+  } while (0)
+  CTX_TRY(cudaMalloc(&c->d_epochs, blk.size()));
+  CTX_TRY(cudaMemcpy(c->d_epochs, blk.data(), blk.size(), cudaMemcpyHostToDevice));
+  CTX_TRY(cudaMalloc(&c->d_src_col, sizeof(int32_t) * (size_t)(n_src > 0 ? n_src : 1)));
+  CTX_TRY(cudaMemcpy(c->d_src_col, d->src_col, sizeof(int32_t) * (size_t)n_src, cudaMemcpyHostToDevice));
+  CTX_TRY(cudaMalloc(&c->d_src_const, sizeof(double) * (size_t)(n_src > 0 ? n_src : 1)));
+  CTX_TRY(cudaMemcpy(c->d_src_const, d->src_const, sizeof(double) * (size_t)n_src, cudaMemcpyHostToDevice));
+  CTX_TRY(cudaMalloc(&c->d_priors, sizeof(rvlp_prior) * (size_t)(d->n_priors > 0 ? d->n_priors : 1)));
+  if (d->n_priors)
+    CTX_TRY(cudaMemcpy(c->d_priors, d->priors, sizeof(rvlp_prior) * (size_t)d->n_priors, cudaMemcpyHostToDevice));
+  P.epochs = reinterpret_cast<const double*>(c->d_epochs);
+  P.src_col = reinterpret_cast<const int32_t*>(c->d_src_col);
+  P.src_const = reinterpret_cast<const double*>(c->d_src_const);
+  P.priors = reinterpret_cast<const rvlp_prior*>(c->d_priors);
+
+  CTX_TRY(cudaDeviceGetAttribute(&c->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  const SmemLayout L = smem_layout(P);
+  c->smem_main = L.total;
+  if (c->smem_main > c->max_smem) {
+    int rc = fail(RVLP_EUNSUPPORTED, "problem needs %d B of shared memory per CTA (> %d): too many epochs",
+                  c->smem_main, c->max_smem);
+    rvlp_ctx_destroy(c);
+    return rc;
+  }
+  CTX_TRY(cudaFuncSetAttribute(logprob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+  CTX_TRY(cudaFuncSetAttribute(rv_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+  if (P.n_hyper) {
+    c->smem_gp = gp_smem(P, L).total;
+    if (c->smem_gp > c->max_smem) {
+      int rc = fail(RVLP_EUNSUPPORTED, "GP problem needs %d B of shared memory per CTA (> %d)", c->smem_gp,
+                    c->max_smem);
+      rvlp_ctx_destroy(c);
+      return rc;
+    }
+    CTX_TRY(cudaFuncSetAttribute(gp_logprob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+  }
+  CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+#undef CTX_TRY
+  *out = c;
+  return RVLP_OK;
+}
+
+void rvlp_ctx_destroy(rvlp_ctx* c) {
+  if (!c) return;
+  DeviceGuard guard(c->device);
+  cudaFree(c->d_epochs);
+  cudaFree(c->d_src_col);
+  cudaFree(c->d_src_const);
+  cudaFree(c->d_priors);
+  cudaFree(c->d_theta);
+  cudaFree(c->d_out);
+  if (c->h_theta) cudaFreeHost(c->h_theta);
+  if (c->h_out) cudaFreeHost(c->h_out);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+static int launch_logprob(rvlp_ctx* c, const double* theta, int64_t S, double* out, double* ll, double* lp,
+                          cudaStream_t st) {
+  if (S == 0) return RVLP_OK;
+  int grid = 0;
+  const int64_t want = ((S + kG - 1) / kG + kWarps - 1) / kWarps;
+  int rc = grid_for(c->device, (const void*)logprob_kernel, c->smem_main, want, &grid);
+  if (rc) return rc;
+  logprob_kernel<<<grid, kThreads, c->smem_main, st>>>(c->P, theta, S, out, ll, lp);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return RVLP_OK;
+}
+
+int rvlp_logprob_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, double* out_dev, void* stream) {
+  if (!c || S < 0 || (S > 0 && (!theta_dev || !out_dev))) return fail(RVLP_EINVAL, "bad arguments");
+  if (c->P.n_hyper) return fail(RVLP_EINVAL, "GP context: call rvlp_gp_logprob_batch");
+  DeviceGuard guard(c->device);
+  return launch_logprob(c, theta_dev, S, out_dev, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int rvlp_logprob_parts_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, double* ll_dev, double* lp_dev,
+                             void* stream) {
+  if (!c || S < 0 || (S > 0 && !theta_dev)) return fail(RVLP_EINVAL, "bad arguments");
+  if (c->P.n_hyper) return fail(RVLP_EINVAL, "GP context not supported here");
+  if (!ll_dev && !lp_dev) return RVLP_OK;
+  DeviceGuard guard(c->device);
+  // ll_out non-null forces the likelihood to be evaluated even for rows the prior rejects
+  return launch_logprob(c, theta_dev, S, nullptr, ll_dev, lp_dev, (cudaStream_t)stream);
+}
+
+int rvlp_logprob_batch_host(rvlp_ctx* c, const double* theta_host, int64_t S, double* out_host) {
+  if (!c || S < 0 || (S > 0 && (!theta_host || !out_host))) return fail(RVLP_EINVAL, "bad arguments");
+  if (S == 0) return RVLP_OK;
+  DeviceGuard guard(c->device);
+  if (S > c->cap_samples) {
+    cudaFree(c->d_theta); cudaFree(c->d_out);
+    if (c->h_theta) cudaFreeHost(c->h_theta);
+    if (c->h_out) cudaFreeHost(c->h_out);
+    c->d_theta = c->d_out = c->h_theta = c->h_out = nullptr;
+    c->cap_samples = 0;
+    const size_t nb = sizeof(double) * (size_t)S * (size_t)(c->P.ndim > 0 ? c->P.ndim : 1);
+    CUDA_TRY(cudaMalloc((void**)&c->d_theta, nb));
+    CUDA_TRY(cudaMalloc((void**)&c->d_out, sizeof(double) * (size_t)S));
+    CUDA_TRY(cudaMallocHost((void**)&c->h_theta, nb));
+    CUDA_TRY(cudaMallocHost((void**)&c->h_out, sizeof(double) * (size_t)S));
+    c->cap_samples = S;
+  }
+  // already page-locked caller buffers (e.g. torch pin_memory) are used in place; pageable ones are
+  // staged through the context's pinned buffers
+  auto is_pinned = [](const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
+  const bool in_pinned = is_pinned(theta_host), out_pinned = is_pinned(out_host);
+  const double* src = in_pinned ? theta_host : c->h_theta;
+  double* dst = out_pinned ? out_host : c->h_out;
+  // chunked so that the H2D of chunk i+1 (and the staging memcpy) overlaps the kernel of chunk i
+  const int64_t chunk = S > (1 << 16) ? (S + 7) / 8 : S;
+  for (int64_t s0 = 0; s0 < S; s0 += chunk) {
+    const int64_t n = (S - s0 < chunk) ? S - s0 : chunk;
+    const size_t off = (size_t)s0 * (size_t)c->P.ndim;
+    const size_t nbytes = sizeof(double) * (size_t)n * (size_t)c->P.ndim;
+    if (!in_pinned) memcpy(c->h_theta + off, theta_host + off, nbytes);
+    CUDA_TRY(cudaMemcpyAsync(c->d_theta + off, src + off, nbytes, cudaMemcpyHostToDevice, c->stream));
+    int rc = c->P.n_hyper ? rvlp_gp_logprob_batch(c, c->d_theta + off, n, c->d_out + s0, c->stream)
+                          : launch_logprob(c, c->d_theta + off, n, c->d_out + s0, nullptr, nullptr, c->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(dst + s0, c->d_out + s0, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost,
+                             c->stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (!out_pinned) memcpy(out_host, c->h_out, sizeof(double) * (size_t)S);
+  return RVLP_OK;
+}
+
+int rvlp_rv_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const double* times_dev, int64_t T,
+                  int32_t component, double* out_dev, void* stream) {
+  if (!c || S < 0 || T < 0) return fail(RVLP_EINVAL, "bad arguments");
+  if (component < RVLP_RV_TOTAL || component >= c->P.n_planets) return fail(RVLP_EINVAL, "bad component %d", component);
+  if (S == 0 || T == 0) return RVLP_OK;
+  if (!theta_dev || !times_dev || !out_dev) return fail(RVLP_EINVAL, "null pointer");
+  DeviceGuard guard(c->device);
+  int grid = 0;
+  const int64_t want = ((S + kG - 1) / kG + kWarps - 1) / kWarps;
+  int rc = grid_for(c->device, (const void*)rv_matrix_kernel, c->smem_main, want, &grid);
+  if (rc) return rc;
+  rv_matrix_kernel<<<grid, kThreads, c->smem_main, (cudaStream_t)stream>>>(c->P, theta_dev, S, times_dev, T,
+                                                                           component, out_dev);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return RVLP_OK;
+}
+
+int rvlp_gp_logprob_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, double* out_dev, void* stream) {
+  if (!c || S < 0 || (S > 0 && (!theta_dev || !out_dev))) return fail(RVLP_EINVAL, "bad arguments");
+  if (c->P.n_hyper != 4) return fail(RVLP_EINVAL, "context was not created with GP hyperparameters");
+  if (S == 0) return RVLP_OK;
+  DeviceGuard guard(c->device);
+  int grid = 0;
+  int rc = grid_for(c->device, (const void*)gp_logprob_kernel, c->smem_gp, S, &grid);
+  if (rc) return rc;
+  gp_logprob_kernel<<<grid, kThreads, c->smem_gp, (cudaStream_t)stream>>>(c->P, theta_dev, S, out_dev);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return RVLP_OK;
+}
+
+int rvlp_kepler_rv(const double* M_dev, int64_t n, double e, double K, double w, double* rv_dev, int device,
+                   void* stream) {
+  if (n < 0 || (n > 0 && (!M_dev || !rv_dev))) return fail(RVLP_EINVAL, "bad arguments");
+  if (n == 0) return RVLP_OK;
+  DeviceGuard guard(device);
+  kepler_rv_kernel<<<simple_grid(n), 256, 0, (cudaStream_t)stream>>>(M_dev, n, e, K, w, rv_dev);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return RVLP_OK;
+}
+
+int rvlp_planet_rv(int32_t par, const double* p5, const double* t_dev, int64_t n, double* rv_dev, int accumulate,
+                   int device, void* stream) {
+  if (par < 0 || par > 3 || !p5) return fail(RVLP_EINVAL, "bad parameterisation / params");
+  const DefaultPars d = to_default(par, p5);
+  if (d.invalid) {   // the reference's ValueError messages, param.py:26-82
+    if (d.conv_error || d.e < 0) return fail(RVLP_EINVAL, d.e < 0 ? "Invalid eccentricity: %g < 0" : "Invalid eccentricity: %g >= 1.0", d.e);
+    if (d.P <= 0) return fail(RVLP_EINVAL, "Invalid period: %g <= 0", d.P);
+    if (d.K <= 0) return fail(RVLP_EINVAL, "Invalid semi-amplitude: %g <= 0", d.K);
+    if (d.e >= 1.0) return fail(RVLP_EINVAL, "Invalid eccentricity: %g >= 1.0", d.e);
+    return fail(RVLP_EINVAL, "Invalid argument of periastron: %g not in [-pi, +pi)", d.w);
+  }
+  if (n < 0 || (n > 0 && (!t_dev || !rv_dev))) return fail(RVLP_EINVAL, "bad arguments");
+  if (n == 0) return RVLP_OK;
+  DeviceGuard guard(device);
+  planet_rv_kernel<<<simple_grid(n), 256, 0, (cudaStream_t)stream>>>(d, t_dev, n, rv_dev, accumulate);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return RVLP_OK;
+}
+
+int rvlp_trend_rv(double gd, double gdd, double t0, const double* t_dev, int64_t n, double* rv_dev, int accumulate,
+                  int device, void* stream) {
+  if (n < 0 || (n > 0 && (!t_dev || !rv_dev))) return fail(RVLP_EINVAL, "bad arguments");
+  if (n == 0) return RVLP_OK;
+  DeviceGuard guard(device);
+  trend_rv_kernel<<<simple_grid(n), 256, 0, (cudaStream_t)stream>>>(gd, gdd, t0, t_dev, n, rv_dev, accumulate);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return RVLP_OK;
+}
+
+int rvlp_convert_to_default(int32_t par, const double* in_dev, int64_t n, double* out_dev, int32_t* valid_dev,
+                            int device, void* stream) {
+  if (par < 0 || par > 3) return fail(RVLP_EINVAL, "bad parameterisation id");
+  if (n < 0 || (n > 0 && (!in_dev || !out_dev))) return fail(RVLP_EINVAL, "bad arguments");
+  if (n == 0) return RVLP_OK;
+  DeviceGuard guard(device);
+  convert_kernel<<<simple_grid(n), 256, 0, (cudaStream_t)stream>>>(par, in_dev, n, out_dev, valid_dev);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return RVLP_OK;
+}
+
+int rvlp_prior_eval(const rvlp_prior* prior, const double* x_dev, int64_t n, double* out_dev, int device,
+                    void* stream) {
+  if (!prior || prior->kind < 0 || prior->kind > RVLP_PRIOR_BETA) return fail(RVLP_EINVAL, "bad prior");
+  if (n < 0 || (n > 0 && (!x_dev || !out_dev))) return fail(RVLP_EINVAL, "bad arguments");
+  if (n == 0) return RVLP_OK;
+  DeviceGuard guard(device);
+  prior_kernel<<<simple_grid(n), 256, 0, (cudaStream_t)stream>>>(*prior, x_dev, n, out_dev);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return RVLP_OK;
+}
+
+int rvlp_measure_fp64_peak(int device, int iters, double* flops_per_s, double* ms_out) {
+  if (!flops_per_s || iters < 1) return fail(RVLP_EINVAL, "bad arguments");
+  DeviceGuard guard(device);
+  int sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int grid = sms * 8;
+  double* d_out = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&d_out, sizeof(double) * (size_t)grid * 256));
+  cudaEvent_t a, b;
+  CUDA_TRY(cudaEventCreate(&a));
+  CUDA_TRY(cudaEventCreate(&b));
+  fp64_peak_kernel<<<grid, 256>>>(d_out, iters / 4 + 1, 0.999999, 1e-7);   // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    CUDA_TRY(cudaEventRecord(a));
+    fp64_peak_kernel<<<grid, 256>>>(d_out, iters, 0.999999, 1e-7);
+    CUDA_TRY(cudaEventRecord(b));
+    CUDA_TRY(cudaEventSynchronize(b));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, a, b));
+    if (ms < best) best = ms;
+    g_launches += 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  const double flops = 2.0 * 64.0 * (double)iters * (double)grid * 256.0;
+  *flops_per_s = flops / (best * 1e-3);
+  if (ms_out) *ms_out = best;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d_out);
+  return RVLP_OK;
+}
+
+}  // extern "C"

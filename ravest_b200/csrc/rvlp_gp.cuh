@@ -1,0 +1,152 @@
+// rvlp_gp.cuh — K3: batched quasi-periodic GP log-posterior (config 5).
+//
+// Replaces GPLogPosterior.log_probability / GPLogLikelihood.__call__
+// (/root/reference/src/ravest/fit.py:7836-7901, 8062-8105) and the kernel of gp.py:126-156.
+// The dense algebra lives in tinygp 0.3.0 (absent, "parity unpinned"): restated as
+//   C_ij = A^2 exp(-Gamma sin^2(pi |t_i - t_j| / P_gp)) exp(-(t_i - t_j)^2 / (2 lambda_e^2))
+//          + delta_ij (sigma_i^2 + jit_i^2),            Gamma = 1 / (2 lambda_p^2)
+//   C = L L^T,  alpha = L^-1 (v - mean),  ll = -1/2 alpha.alpha - sum log L_ii - N/2 log 2 pi.
+//
+// One CTA per sample.  The packed lower triangle of C (plus the residual as an extra row, so
+// the factorisation's column sweeps produce alpha for free) sits in shared memory:
+// (N+1)(N+2)/2 doubles = 59 KB at N = 120, three CTAs per SM.  Right-looking Cholesky with
+// the trailing update spread over the CTA.  fp64 throughout.
+#pragma once
+#include "rvlp_kernels.cuh"
+
+namespace rvlp {
+
+__host__ __device__ inline int gp_tri_doubles(int N) { return (N + 1) * (N + 2) / 2; }
+__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+struct GpSmem {
+  int off_tri, off_red, total;
+};
+__host__ __device__ inline GpSmem gp_smem(const DevProblem& P, const SmemLayout& L) {
+  GpSmem G;
+  int o = (L.total + 15) & ~15;
+  G.off_tri = o; o += gp_tri_doubles(P.n_epochs) * 8;
+  G.off_red = o; o += 64 * 8;
+  G.total = o;
+  return G;
+}
+
+__global__ void __launch_bounds__(kThreads)
+gp_logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout L = smem_layout(P);
+  const GpSmem G = gp_smem(P, L);
+  stage_problem(P, L, smem);
+  const Tables T = tables_of(L, smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
+  double* scratch = reinterpret_cast<double*>(smem + L.off_scratch);   // warp 0's slot, sample g = 0
+  double* Cm = reinterpret_cast<double*>(smem + G.off_tri);
+  double* red = reinterpret_cast<double*>(smem + G.off_red);
+  const int N = P.n_epochs;
+
+  for (int64_t s = blockIdx.x; s < S; s += gridDim.x) {
+    if (warp == 0) sample_prologue(P, T, theta, s, s + 1, scratch, rec, lane, true);
+    __syncthreads();
+    const double* sr = scratch;
+    const int flags = __double2loint(sr[1]);
+    const double lp = sr[0], lhp = sr[4];
+    if (flags & (F_JIT | F_HYPER | F_PRIOR)) {               // fit.py:7857-7886
+      if (tid == 0) out[s] = -INFINITY;
+      __syncthreads();
+      continue;
+    }
+    if (flags & F_PLANET) {                                  // fit.py:8022-8024, 8082-8083
+      if (tid == 0) {
+        double r = -INFINITY + lp + lhp;
+        r += P.jacobian;
+        r += P.renorm;
+        out[s] = r;
+      }
+      __syncthreads();
+      continue;
+    }
+    const double* row = theta + s * P.ndim;
+    const double A = model_param(T, row, P.n_model + 0), le = model_param(T, row, P.n_model + 1);
+    const double lpp = model_param(T, row, P.n_model + 2), Pg = model_param(T, row, P.n_model + 3);
+    const double gamma = 1.0 / (2.0 * (lpp * lpp));          // gp.py:152
+    const double A2 = A * A, inv_le = 1.0 / le, inv_Pg = 1.0 / Pg;
+
+    // residual row (index N): v - (planets + trend + gamma_inst)   fit.py:7994-8043, 8059
+    int nonfinite = 0;
+    for (int i = tid; i < N; i += kThreads) {
+      double tt[1] = {T.t[i]}, rv[1];
+      model_rv<1>(P, sr, tt, rv, -1, true);
+      const double mean = rv[0] + sr[kHdr + T.inst[i]];
+      if (!(fabs(mean) <= 1.79769313486231570e308)) nonfinite = 1;
+      Cm[tri(N, i)] = T.v[i] - mean;
+    }
+    // covariance, packed lower triangle                        gp.py:145-156, fit.py:8094-8096
+    const int npairs = N * (N + 1) / 2;
+    for (int p = tid; p < npairs; p += kThreads) {
+      int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+      while (tri(i + 1, 0) <= p) ++i;
+      while (tri(i, 0) > p) --i;
+      const int j = p - tri(i, 0);
+      const double tau = T.t[i] - T.t[j];
+      const double sn = sinpi(fabs(tau) * inv_Pg);
+      const double q = tau * inv_le;
+      double c = A2 * exp(-gamma * (sn * sn)) * exp(-0.5 * (q * q));
+      if (i == j) c += T.e2[i] + sr[kHdr + P.n_inst + T.inst[i]];
+      Cm[p] = c;
+    }
+    if (__syncthreads_or(nonfinite)) {                       // fit.py:8082-8083
+      if (tid == 0) {
+        double r = -INFINITY + lp + lhp;
+        r += P.jacobian;
+        r += P.renorm;
+        out[s] = r;
+      }
+      __syncthreads();
+      continue;
+    }
+    // right-looking Cholesky on rows 0..N (row N = residual -> alpha)
+    double logdet_part = 0.0;
+    for (int j = 0; j < N; ++j) {
+      const double djj = sqrt(Cm[tri(j, j)]);                // NaN when not positive definite (as jax)
+      const double inv = 1.0 / djj;
+      if (tid == 0) logdet_part += log(djj);
+      __syncthreads();                                       // everyone has read C_jj
+      for (int i = j + 1 + tid; i <= N; i += kThreads) Cm[tri(i, j)] *= inv;
+      if (tid == 0) Cm[tri(j, j)] = djj;
+      __syncthreads();
+      // trailing update: C_ik -= L_ij L_kj for j < k <= i <= N (diagonal of row N not needed)
+      const int m = N - j;                                   // rows j+1..N
+      const int cnt = m * (m + 1) / 2;
+      for (int p = tid; p < cnt; p += kThreads) {
+        int a = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+        while ((a + 1) * (a + 2) / 2 <= p) ++a;
+        while (a * (a + 1) / 2 > p) --a;
+        const int b = p - a * (a + 1) / 2;
+        const int i = j + 1 + a, k = j + 1 + b;
+        if (i == N && k == N) continue;
+        Cm[tri(i, k)] = fma(-Cm[tri(i, j)], Cm[tri(k, j)], Cm[tri(i, k)]);
+      }
+      __syncthreads();
+    }
+    // quad = alpha . alpha
+    double q = 0.0;
+    for (int i = tid; i < N; i += kThreads) q = fma(Cm[tri(N, i)], Cm[tri(N, i)], q);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) red[warp] = q;
+    __syncthreads();
+    if (tid == 0) {
+      double quad = 0.0;
+      for (int w = 0; w < kWarps; ++w) quad += red[w];
+      const double ll = -0.5 * quad - logdet_part - 0.5 * (double)N * kLog2Pi;
+      double r = ll + lp + lhp;                              // fit.py:7898-7900
+      r += P.jacobian;
+      r += P.renorm;
+      out[s] = r;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace rvlp

@@ -1,0 +1,461 @@
+// rvlp_kernels.cuh — the sm_100a kernels of the batched RV log-probability path.
+//
+// Work decomposition: ONE WARP owns one sample at a time.  The 32 lanes are
+// 32 epochs; the warp walks the epoch axis in strides of 32*W (W = 2 epochs per lane in
+// flight for ILP), looping over the planets innermost.  Consequences:
+//   * every per-(sample, planet) quantity - eccentricity, the solver's iteration counts, the
+//     circular-orbit branch - is warp-uniform: no divergence anywhere in the hot loop;
+//   * the chi^2 + log-det sum of a sample is 32 lane-partials (fixed epoch order) folded by one
+//     xor-butterfly: the bits of out[s] depend on (theta[s], epochs) only, never on S, the
+//     grid, the shard or the GPU count;
+//   * per-sample constants live in a small per-warp shared-memory record and are read back as
+//     broadcasts; the epoch arrays are staged once per CTA into shared memory by a TMA bulk
+//     copy (cp.async.bulk -> UBLKCP).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "rvlp_math.cuh"
+
+namespace rvlp {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kW = 2;             // epochs per lane in flight
+constexpr int kG = 4;             // samples whose prologue a warp does together
+constexpr int kPlanetRec = 16;    // doubles per planet in the sample record
+constexpr double kLog2Pi = 1.8378770664093453;   // np.log(2*np.pi), fit.py:3595
+
+// Device view of a context: descriptor tables + resident epoch arrays (all device pointers).
+struct DevProblem {
+  int n_planets, par, n_inst, ndim, n_priors, n_hyper, n_model, n_epochs, n_pad;
+  double t0, jacobian, renorm;
+  const int32_t* src_col;
+  const double* src_const;
+  const rvlp_prior* priors;
+  const double* epochs;   // [t | vel | err2] x n_pad doubles, then n_pad int32 instrument ids
+};
+
+constexpr int kHdr = 6;           // sample record header doubles
+__host__ __device__ inline int sample_rec_doubles(int n_planets, int n_inst) {
+  return kHdr + 2 * n_inst + kPlanetRec * n_planets;
+}
+// sample record: [0] lp  [1] flags  [2] gd  [3] gdd  [4] lhp  [5] -  [6..) gamma[n_inst]  jit2[n_inst]  planets
+// planet record: n tp e A B C w K | tol plan(bits) P Kraw e w tp invalid
+enum { F_JIT = 1, F_PLANET = 2, F_PRIOR = 4, F_HYPER = 8, F_SKIP = 16 };
+
+struct SmemLayout {
+  int off_t, off_v, off_e2, off_inst, off_priors, off_srccol, off_srcconst, off_scratch, total;
+};
+
+__host__ __device__ inline SmemLayout smem_layout(const DevProblem& P) {
+  SmemLayout L;
+  int o = 0;
+  L.off_t = o; o += P.n_pad * 8;
+  L.off_v = o; o += P.n_pad * 8;
+  L.off_e2 = o; o += P.n_pad * 8;
+  L.off_inst = o; o += P.n_pad * 4;
+  o = (o + 15) & ~15;
+  L.off_priors = o; o += P.n_priors * (int)sizeof(rvlp_prior);
+  L.off_srcconst = o; o += (P.n_model + P.n_hyper) * 8;
+  L.off_srccol = o; o += (P.n_model + P.n_hyper) * 4;
+  o = (o + 15) & ~15;
+  L.off_scratch = o; o += kWarps * kG * sample_rec_doubles(P.n_planets, P.n_inst) * 8;
+  L.total = o + 16;   // + mbarrier
+  return L;
+}
+
+// ------------------------------------------------------------------ TMA bulk copy helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+
+// Stage the resident epoch arrays + descriptor tables into shared memory (once per CTA).
+__device__ __forceinline__ void stage_problem(const DevProblem& P, const SmemLayout& L, unsigned char* smem) {
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.total - 16);
+  const uint32_t epoch_bytes = (uint32_t)(P.n_pad * 28);   // 3 x 8 + 4 per epoch, n_pad % 64 == 0
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, epoch_bytes);
+    bulk_g2s(smem + L.off_t, P.epochs, epoch_bytes, bar);
+  }
+  // small tables: plain loads
+  {
+    const int nw = P.n_priors * (int)(sizeof(rvlp_prior) / 8);
+    const double* src = reinterpret_cast<const double*>(P.priors);
+    double* dst = reinterpret_cast<double*>(smem + L.off_priors);
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+    const int nm = P.n_model + P.n_hyper;
+    double* dc = reinterpret_cast<double*>(smem + L.off_srcconst);
+    int* di = reinterpret_cast<int*>(smem + L.off_srccol);
+    for (int i = threadIdx.x; i < nm; i += blockDim.x) {
+      dc[i] = P.src_const[i];
+      di[i] = P.src_col[i];
+    }
+  }
+  mbar_wait(bar, 0);
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ per-sample prologue
+struct Tables {
+  const double* t;
+  const double* v;
+  const double* e2;
+  const int* inst;
+  const rvlp_prior* priors;
+  const double* src_const;
+  const int* src_col;
+};
+
+__device__ __forceinline__ Tables tables_of(const SmemLayout& L, unsigned char* smem) {
+  Tables T;
+  T.t = reinterpret_cast<const double*>(smem + L.off_t);
+  T.v = reinterpret_cast<const double*>(smem + L.off_v);
+  T.e2 = reinterpret_cast<const double*>(smem + L.off_e2);
+  T.inst = reinterpret_cast<const int*>(smem + L.off_inst);
+  T.priors = reinterpret_cast<const rvlp_prior*>(smem + L.off_priors);
+  T.src_const = reinterpret_cast<const double*>(smem + L.off_srcconst);
+  T.src_col = reinterpret_cast<const int*>(smem + L.off_srccol);
+  return T;
+}
+
+__device__ __forceinline__ double model_param(const Tables& T, const double* row, int i) {
+  const int c = T.src_col[i];
+  return c >= 0 ? row[c] : T.src_const[i];
+}
+
+// Phase A: one lane per (sample, planet): conversion, validity, Kepler constants.
+// Phase B: one lane per sample: jitter check, gamma / jitter^2, priors in order.
+__device__ __forceinline__ void sample_prologue(const DevProblem& P, const Tables& T, const double* theta,
+                                                int64_t s0, int64_t S, double* scratch, int rec, int lane,
+                                                bool with_priors) {
+  const int npl = P.n_planets;
+  for (int task = lane; task < kG * npl; task += 32) {
+    const int g = task / npl, k = task - g * npl;
+    const int64_t s = s0 + g;
+    if (s >= S) continue;
+    const double* row = theta + s * P.ndim;
+    double in[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) in[q] = model_param(T, row, 5 * k + q);
+    const DefaultPars d = to_default(P.par, in);
+    double* pr = scratch + g * rec + kHdr + 2 * P.n_inst + k * kPlanetRec;
+    PlanetConst pc = planet_const(d);
+    const SolverPlan plan = plan_for(d.e);
+    pr[0] = pc.n; pr[1] = pc.tp; pr[2] = pc.e; pr[3] = pc.A; pr[4] = pc.B; pr[5] = pc.C;
+    pr[6] = pc.w; pr[7] = pc.K; pr[8] = plan.tol;
+    pr[9] = __hiloint2double(plan.n64, plan.n32);
+    pr[10] = d.P; pr[11] = d.K; pr[12] = d.e; pr[13] = d.w; pr[14] = d.tp;
+    pr[15] = d.invalid ? 1.0 : 0.0;
+  }
+  __syncwarp();
+  if (lane < kG && s0 + lane < S) {
+    const int g = lane;
+    const double* row = theta + (s0 + g) * P.ndim;
+    double* sr = scratch + g * rec;
+    const int i_gd = 5 * npl, i_g = i_gd + 2, i_jit = i_g + P.n_inst;
+    int flags = 0;
+    sr[2] = model_param(T, row, i_gd);
+    sr[3] = model_param(T, row, i_gd + 1);
+    for (int j = 0; j < P.n_inst; ++j) {
+      const double jit = model_param(T, row, i_jit + j);
+      if (jit < 0) flags |= F_JIT;                          // fit.py:3465-3468
+      sr[kHdr + j] = model_param(T, row, i_g + j);
+      sr[kHdr + P.n_inst + j] = jit * jit;                     // fit.py:3654
+    }
+    const double* planets = sr + kHdr + 2 * P.n_inst;
+    for (int k = 0; k < npl; ++k)
+      if (planets[k * kPlanetRec + 15] != 0.0) flags |= F_PLANET;
+    if (P.n_hyper) {                                        // gp.py:98-108
+      for (int k = 0; k < 4; ++k) {
+        const double h = model_param(T, row, P.n_model + k);
+        if (!(fabs(h) <= 1.79769313486231570e308) || h <= 0) flags |= F_HYPER;
+      }
+    }
+    double lp = 0.0, lhp = 0.0;
+    if (with_priors) {
+      for (int j = 0; j < P.n_priors; ++j) {                // fit.py:3685-3691
+        const rvlp_prior& pr = T.priors[j];
+        double x;
+        if (pr.target == RVLP_TARGET_COLUMN) x = row[pr.index];
+        else x = planets[pr.index * kPlanetRec + 9 + pr.target];   // P K e w tp at [10..14]
+        const double v = prior_logpdf(pr, x);
+        if (pr.is_hyper) lhp += v; else lp += v;
+      }
+      // a failed Tc->Tp conversion makes a derived Tp NaN, i.e. lp non-finite: fit.py:3478-3482
+      if (!(fabs(lp) <= 1.79769313486231570e308)) flags |= F_PRIOR;
+      if (!(fabs(lhp) <= 1.79769313486231570e308)) flags |= F_PRIOR;
+    }
+    sr[0] = lp;
+    sr[1] = __hiloint2double(0, flags);
+    sr[4] = lhp;
+  }
+  __syncwarp();
+}
+
+// RV of every planet + trend at W epochs per lane (fit.py:3613-3636 / model.py:639-664).
+template <int W>
+__device__ __forceinline__ void model_rv(const DevProblem& P, const double* sr, const double (&tt)[W],
+                                         double (&rv)[W], int only_planet, bool with_trend) {
+  const double* planets = sr + kHdr + 2 * P.n_inst;
+#pragma unroll
+  for (int j = 0; j < W; ++j) rv[j] = 0.0;
+  for (int k = 0; k < P.n_planets; ++k) {
+    if (only_planet >= 0 && k != only_planet) continue;
+    const double* pr = planets + k * kPlanetRec;
+    PlanetConst pc;
+    pc.n = pr[0]; pc.tp = pr[1]; pc.e = pr[2]; pc.A = pr[3]; pc.B = pr[4]; pc.C = pr[5];
+    pc.w = pr[6]; pc.K = pr[7];
+    SolverPlan plan;
+    plan.tol = pr[8];
+    plan.n32 = __double2loint(pr[9]);
+    plan.n64 = __double2hiint(pr[9]);
+    double r[W];
+    planet_rv<W>(pc, plan, tt, r);
+#pragma unroll
+    for (int j = 0; j < W; ++j) rv[j] += r[j];
+  }
+  if (with_trend) {                                          // model.py:483-509
+    const double gd = sr[2], gdd = sr[3];
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const double dt = tt[j] - P.t0;
+      double tr = 0.0;
+      if (gd != 0) tr += gd * dt;
+      if (gdd != 0) tr += gdd * (dt * dt);
+      rv[j] += tr;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K1: log-probability
+__global__ void __launch_bounds__(kThreads)
+logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double* __restrict__ out,
+               double* __restrict__ ll_out, double* __restrict__ lp_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout L = smem_layout(P);
+  stage_problem(P, L, smem);
+  const Tables T = tables_of(L, smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
+  double* scratch = reinterpret_cast<double*>(smem + L.off_scratch) + warp * kG * rec;
+  const int64_t n_batches = (S + kG - 1) / kG;
+  const int64_t gw = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
+
+  for (int64_t b = gw; b < n_batches; b += nw) {
+    const int64_t s0 = b * kG;
+    sample_prologue(P, T, theta, s0, S, scratch, rec, lane, true);
+    for (int g = 0; g < kG; ++g) {
+      const int64_t s = s0 + g;
+      if (s >= S) break;
+      const double* sr = scratch + g * rec;
+      const int flags = __double2loint(sr[1]);
+      const double lp = sr[0];
+      double ll;
+      if (flags & F_PLANET) {
+        ll = -INFINITY;                                      // fit.py:3625-3627
+      } else if ((flags & (F_JIT | F_PRIOR)) && ll_out == nullptr) {
+        ll = 0.0;                                            // result is -inf regardless: skip the work
+      } else {
+        double acc = 0.0;
+        for (int base = 0; base < P.n_pad; base += 32 * kW) {
+          double tt[kW], rv[kW];
+          int idx[kW];
+#pragma unroll
+          for (int j = 0; j < kW; ++j) {
+            idx[j] = base + j * 32 + lane;
+            tt[j] = T.t[idx[j]];
+          }
+          model_rv<kW>(P, sr, tt, rv, -1, true);
+#pragma unroll
+          for (int j = 0; j < kW; ++j) {
+            const int in = T.inst[idx[j]];
+            const double tot = rv[j] + sr[kHdr + in];           // fit.py:3642-3644
+            const double var = T.e2[idx[j]] + sr[kHdr + P.n_inst + in];
+            const double res = tot - T.v[idx[j]];
+            const double term = res * res / var + (kLog2Pi + log(var));   // fit.py:3655-3658
+            if (idx[j] < P.n_epochs) acc += term;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        ll = -0.5 * acc;
+      }
+      if (lane == 0) {
+        double r;
+        if (flags & (F_JIT | F_PRIOR | F_HYPER)) {
+          r = -INFINITY;                                     // fit.py:3468, 3480-3482
+        } else {
+          r = ll + lp;                                       // fit.py:3492-3495
+          r += P.jacobian;
+          r += P.renorm;
+        }
+        if (out) out[s] = r;
+        if (ll_out) ll_out[s] = ll;
+        if (lp_out) lp_out[s] = lp;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ K2: RV matrix (fit.py:2690-2824)
+__global__ void __launch_bounds__(kThreads)
+rv_matrix_kernel(DevProblem P, const double* __restrict__ theta, int64_t S,
+                 const double* __restrict__ times, int64_t T_n, int component, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout L = smem_layout(P);
+  stage_problem(P, L, smem);
+  const Tables T = tables_of(L, smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
+  double* scratch = reinterpret_cast<double*>(smem + L.off_scratch) + warp * kG * rec;
+  const int64_t n_batches = (S + kG - 1) / kG;
+  const int64_t gw = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
+  const int only = component >= 0 ? component : (component == RVLP_RV_TREND ? P.n_planets : -1);
+  const bool trend = component < 0;
+
+  for (int64_t b = gw; b < n_batches; b += nw) {
+    const int64_t s0 = b * kG;
+    sample_prologue(P, T, theta, s0, S, scratch, rec, lane, false);
+    for (int g = 0; g < kG; ++g) {
+      const int64_t s = s0 + g;
+      if (s >= S) break;
+      const double* sr = scratch + g * rec;
+      const double* planets = sr + kHdr + 2 * P.n_inst;
+      bool bad = false;
+      for (int k = 0; k < P.n_planets; ++k)
+        if ((only < 0 || k == only) && planets[k * kPlanetRec + 15] != 0.0) bad = true;
+      double* orow = out + s * T_n;
+      for (int64_t base = 0; base < T_n; base += 32 * kW) {
+        double tt[kW], rv[kW];
+        int64_t idx[kW];
+#pragma unroll
+        for (int j = 0; j < kW; ++j) {
+          idx[j] = base + j * 32 + lane;
+          tt[j] = times[idx[j] < T_n ? idx[j] : T_n - 1];
+        }
+        if (bad) {
+#pragma unroll
+          for (int j = 0; j < kW; ++j) rv[j] = NAN;
+        } else {
+          model_rv<kW>(P, sr, tt, rv, only, trend);
+        }
+#pragma unroll
+        for (int j = 0; j < kW; ++j)
+          if (idx[j] < T_n) orow[idx[j]] = rv[j];
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ small stateless kernels
+// model.py:173-243 on raw mean anomalies, one (e, K, w) for the whole array.
+__global__ void kepler_rv_kernel(const double* __restrict__ M, int64_t n, double e, double K, double w,
+                                 double* __restrict__ rv) {
+  DefaultPars d;
+  d.P = 2 * PI_D; d.K = K; d.e = e; d.w = w; d.tp = 0.0; d.conv_error = false; d.invalid = false;
+  PlanetConst pc = planet_const(d);
+  pc.n = 1.0;                      // M = 1.0 * (M - 0.0) is exact
+  const SolverPlan plan = plan_for(e);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double tt[1] = {M[i]}, r[1];
+    planet_rv<1>(pc, plan, tt, r);
+    rv[i] = r[0];
+  }
+}
+
+// model.py:259-275 + 329-354 for one planet given default-space parameters (validated on host side
+// of the ABI via convert kernel); accumulate != 0 adds into rv (Star.radial_velocity, model.py:659-662).
+__global__ void planet_rv_kernel(DefaultPars d, const double* __restrict__ t, int64_t n,
+                                 double* __restrict__ rv, int accumulate) {
+  const PlanetConst pc = planet_const(d);
+  const SolverPlan plan = plan_for(d.e);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double tt[1] = {t[i]}, r[1];
+    planet_rv<1>(pc, plan, tt, r);
+    rv[i] = accumulate ? rv[i] + r[0] : r[0];
+  }
+}
+
+__global__ void trend_rv_kernel(double gd, double gdd, double t0, const double* __restrict__ t, int64_t n,
+                                double* __restrict__ rv, int accumulate) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double dt = t[i] - t0;
+    double tr = 0.0;
+    if (gd != 0) tr += gd * dt;
+    if (gdd != 0) tr += gdd * (dt * dt);
+    rv[i] = accumulate ? rv[i] + tr : tr;
+  }
+}
+
+__global__ void convert_kernel(int par, const double* __restrict__ in, int64_t n, double* __restrict__ out,
+                               int32_t* __restrict__ valid) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double v[5];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) v[q] = in[i * 5 + q];
+    const DefaultPars d = to_default(par, v);
+    out[i * 5 + 0] = d.P; out[i * 5 + 1] = d.K; out[i * 5 + 2] = d.e; out[i * 5 + 3] = d.w;
+    out[i * 5 + 4] = d.tp;
+    if (valid) valid[i] = d.invalid ? 0 : 1;
+  }
+}
+
+__global__ void prior_kernel(rvlp_prior pr, const double* __restrict__ x, int64_t n, double* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = prior_logpdf(pr, x[i]);
+}
+
+// Dependent-free DFMA loop: 8 independent chains per thread, 2 flops per DFMA.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+         x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+}  // namespace rvlp

@@ -1,0 +1,302 @@
+"""LogLikelihood / LogPrior / LogPosterior (+ GP twins) — the drop-in boundary.
+
+Host mirror of `ravest.fit` (fit.py:3228-3691, 7596-8105): same constructor arguments, same
+scalar call conventions (`log_probability(dict) -> float`, `-inf` for invalid values, never
+raising for bad values), plus the new batched entry the reference lacks:
+
+    log_probability_batch(theta[S, ndim]) -> [S]
+
+`theta` columns follow `free_params_names` (GP: + `free_hyperparams_names`, fit.py:4978) — this
+is emcee's `vectorize=True` contract.  A CUDA fp64 tensor in gives a CUDA tensor out (no host
+round trip); a NumPy array in goes through the host-buffer C-ABI call and returns NumPy.
+All arithmetic is in the sm_100a kernels; the objects pickle (spawn pools) by dropping their
+device context and rebuilding it lazily.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Callable, Dict
+
+import numpy as np
+
+from . import _lib
+from .descriptor import Descriptor, instrument_indices
+from .gp import GPKernel
+from .param import Parameterisation
+from .prior import Uniform, _Prior
+
+
+def _par_str(parameterisation) -> str:
+    return parameterisation.parameterisation if isinstance(parameterisation, Parameterisation) else str(parameterisation)
+
+
+def classify_planet_case(letter: str, parameterisation: str, priors: dict, free_params_names) -> str:
+    """fit.py:3306-3368."""
+    if "secosw" not in parameterisation:
+        return "CASE_1"
+    if f"secosw_{letter}" not in free_params_names:
+        return "CASE_1"
+    sc, ss, ek, wk = f"secosw_{letter}", f"sesinw_{letter}", f"e_{letter}", f"w_{letter}"
+    if sc in priors and ss in priors:
+        a, b = priors[sc], priors[ss]
+        if (isinstance(a, Uniform) and isinstance(b, Uniform) and a.lower == -1 and a.upper == 1
+                and b.lower == -1 and b.upper == 1):
+            return "CASE_2"
+        raise NotImplementedError(
+            f"Unsupported priors on (secosw_{letter}, sesinw_{letter}): {a!r}, {b!r}. Only Uniform(-1, 1) priors "
+            "on (secosw, sesinw) are supported for evidence-correct log-posterior corrections. A separable, "
+            "rotationally-symmetric belief about eccentricity can always be re-expressed as a prior on e instead - "
+            f"place priors on (e_{letter}, w_{letter}) using one of Ravest's eccentricity priors (HalfNormal, "
+            "Rayleigh, VanEylen19Mixture, Beta, EccentricityUniform, TruncatedNormal).")
+    elif ek in priors and wk in priors:
+        return "CASE_3"
+    raise RuntimeError(f"Could not classify log-posterior correction case for planet '{letter}': "
+                       "no priors found on either (secosw, sesinw) or (e, w).")
+
+
+def compute_logprob_corrections(planet_letters, parameterisation: str, priors: dict, free_params_names):
+    """fit.py:3370-3397 — (sum of Jacobians, sum of renormalisations, per-planet breakdown)."""
+    log_jac = float(np.log(2)) if "secosw" in parameterisation else 0.0      # param.py:428-435
+    total_j = total_r = 0.0
+    breakdown = {}
+    for letter in planet_letters:
+        case = classify_planet_case(letter, parameterisation, priors, free_params_names)
+        jac = log_jac if case == "CASE_3" else 0.0
+        ren = float(np.log(4.0 / np.pi)) if case == "CASE_2" else 0.0
+        total_j += jac
+        total_r += ren
+        breakdown[letter] = {"case": case, "jacobian": jac, "renorm": ren}
+        logging.info(f"Planet {letter}: log-posterior correction case {case} (jacobian={jac}, renorm={ren})")
+    return total_j, total_r, breakdown
+
+
+class LogPrior:
+    """fit.py:3663-3691 — sum of the priors of the given params, in dict order."""
+
+    def __init__(self, priors: dict) -> None:
+        self.priors = priors
+
+    def __call__(self, params: Dict[str, float]) -> float:
+        lp = 0
+        for name in params:
+            lp += self.priors[name](params[name])
+        return lp
+
+
+class _DeviceBacked:
+    """Lazy, picklable ownership of an rvlp context."""
+
+    _ctx = None
+
+    def _make_descriptor(self) -> Descriptor:
+        raise NotImplementedError
+
+    @property
+    def ctx(self) -> "_lib.Context":
+        if self._ctx is None:
+            self._desc = self._make_descriptor()
+            idx = instrument_indices(self.instrument, self.unique_instruments)
+            self._ctx = _lib.Context(self._desc, self.time, self.vel, self.velerr, idx)
+        return self._ctx
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st.pop("_ctx", None)
+        st.pop("_desc", None)
+        return st
+
+    def _eval_batch(self, theta):
+        torch = _lib._torch()
+        if isinstance(theta, torch.Tensor):
+            return self.ctx.logprob(theta)
+        return self.ctx.logprob_host(np.asarray(theta, dtype=np.float64))
+
+
+class LogLikelihood(_DeviceBacked):
+    """fit.py:3529-3660 — white-noise Gaussian log-likelihood of ALL parameters."""
+
+    def __init__(self, time, vel, velerr, instrument, unique_instruments, t0, planet_letters,
+                 parameterisation: Parameterisation) -> None:
+        self.time, self.vel, self.velerr = time, vel, velerr
+        self.instrument, self.unique_instruments, self.t0 = instrument, unique_instruments, t0
+        self.planet_letters, self.parameterisation = planet_letters, parameterisation
+        self._gamma_keys = [f"g_{i}" for i in self.unique_instruments]
+        self._jitter_keys = [f"jit_{i}" for i in self.unique_instruments]
+
+    @property
+    def param_names(self) -> list[str]:
+        names = []
+        for L in self.planet_letters:
+            names += [f"{p}_{L}" for p in self.parameterisation.pars]
+        return names + ["gd", "gdd"] + self._gamma_keys + self._jitter_keys
+
+    def _make_descriptor(self) -> Descriptor:
+        # every model parameter is a column, no priors, no corrections: out = ll + 0
+        return Descriptor(self.planet_letters, _par_str(self.parameterisation), {}, {}, self.param_names,
+                          self.unique_instruments, self.t0)
+
+    def batch(self, theta):
+        """theta[S, n_model] in `param_names` order -> ll[S]."""
+        th = _lib.as_cuda_f64(theta)
+        ll, _ = self.ctx.logprob_parts(th)
+        return ll
+
+    def __call__(self, params: Dict[str, float]) -> float:
+        row = np.array([[float(params[n]) for n in self.param_names]])
+        return float(self.batch(row)[0])
+
+
+class LogPosterior(_DeviceBacked):
+    """fit.py:3228-3526."""
+
+    def __init__(self, planet_letters, parameterisation: Parameterisation, priors: dict, fixed_params: dict,
+                 free_params_names, time, vel, velerr, instrument, unique_instruments, t0) -> None:
+        self.planet_letters = planet_letters
+        self.parameterisation = parameterisation
+        self.priors = priors
+        self.fixed_params = fixed_params
+        self.free_params_names = free_params_names
+        self.time, self.vel, self.velerr = time, vel, velerr
+        self.instrument, self.unique_instruments, self.t0 = instrument, unique_instruments, t0
+        self.log_likelihood = LogLikelihood(time, vel, velerr, instrument, unique_instruments, t0,
+                                            planet_letters, parameterisation)
+        self.log_prior = LogPrior(self.priors)
+        (self._logprob_jacobian_correction, self._logprob_prior_renorm_correction,
+         self._logprob_correction_breakdown) = compute_logprob_corrections(
+            planet_letters, _par_str(parameterisation), priors, free_params_names)
+
+    def _make_descriptor(self) -> Descriptor:
+        return Descriptor(self.planet_letters, _par_str(self.parameterisation), self.priors, self.fixed_params,
+                          self.free_params_names, self.unique_instruments, self.t0,
+                          jacobian=self._logprob_jacobian_correction,
+                          renorm=self._logprob_prior_renorm_correction)
+
+    # -- the new batched boundary ----------------------------------------------------
+    def log_probability_batch(self, theta):
+        return self._eval_batch(theta)
+
+    def log_probability_parts_batch(self, theta):
+        """(log-likelihood, log-prior) per row, for diagnostics / information criteria."""
+        return self.ctx.logprob_parts(_lib.as_cuda_f64(theta))
+
+    # -- the reference's scalar conventions ------------------------------------------
+    def log_probability(self, free_params_dict: Dict[str, float]) -> float:
+        """fit.py:3448-3495."""
+        row = np.array([[float(free_params_dict[n]) for n in self.free_params_names]])
+        return float(self.ctx.logprob_host(row)[0])
+
+    def _negative_log_probability_for_MAP(self, free_params_vals) -> float:
+        """fit.py:3497-3526."""
+        neg = -float(self.ctx.logprob_host(np.asarray(free_params_vals, dtype=np.float64).reshape(1, -1))[0])
+        if not np.isfinite(neg):
+            return 1e30
+        return neg
+
+    def _convert_params_for_prior_evaluation(self, free_params_dict: dict) -> Dict[str, float]:
+        """fit.py:3399-3446 (host-side helper used by walker validation, fit.py:1059)."""
+        prior_keys, free_keys = set(self.priors.keys()), set(self.free_params_names)
+        if prior_keys == free_keys:
+            return free_params_dict
+        out = {k: v for k, v in free_params_dict.items() if k in prior_keys}
+        allp = self.fixed_params | free_params_dict
+        for L in self.planet_letters:
+            pp = {par: allp[f"{par}_{L}"] for par in self.parameterisation.pars}
+            d = self.parameterisation.convert_pars_to_default_parameterisation(pp)
+            for k, v in d.items():
+                if f"{k}_{L}" in prior_keys:
+                    out[f"{k}_{L}"] = v
+        return out
+
+
+class GPLogLikelihood(_DeviceBacked):
+    """fit.py:7942-8105 — quasi-periodic GP likelihood of ALL params + hyperparams."""
+
+    def __init__(self, time, vel, velerr, t0, instrument, unique_instruments, planet_letters,
+                 parameterisation: Parameterisation, gp_kernel: GPKernel) -> None:
+        self.time, self.vel, self.velerr, self.t0 = time, vel, velerr, t0
+        self.instrument, self.unique_instruments = instrument, unique_instruments
+        self.planet_letters, self.parameterisation, self.gp_kernel = planet_letters, parameterisation, gp_kernel
+
+    @property
+    def param_names(self) -> list[str]:
+        names = []
+        for L in self.planet_letters:
+            names += [f"{p}_{L}" for p in self.parameterisation.pars]
+        return (names + ["gd", "gdd"] + [f"g_{i}" for i in self.unique_instruments]
+                + [f"jit_{i}" for i in self.unique_instruments])
+
+    def _make_descriptor(self) -> Descriptor:
+        return Descriptor(self.planet_letters, _par_str(self.parameterisation), {}, {}, self.param_names,
+                          self.unique_instruments, self.t0, hyperpriors={}, fixed_hyperparams={},
+                          free_hyperparams_names=self.gp_kernel.get_expected_hyperparams())
+
+    def __call__(self, params: Dict[str, float], hyperparams: Dict[str, float]) -> float:
+        names = self.param_names + self.gp_kernel.get_expected_hyperparams()
+        both = dict(params) | dict(hyperparams)
+        row = np.array([[float(both[n]) for n in names]])
+        return float(self.ctx.logprob_host(row)[0])
+
+
+class GPLogPosterior(_DeviceBacked):
+    """fit.py:7596-7939."""
+
+    def __init__(self, planet_letters, parameterisation: Parameterisation, gp_kernel: GPKernel, priors: dict,
+                 hyperpriors: dict, fixed_params: dict, fixed_hyperparams: dict, free_params_names,
+                 free_hyperparams_names, time, vel, velerr, t0, instrument, unique_instruments) -> None:
+        self.planet_letters, self.parameterisation, self.gp_kernel = planet_letters, parameterisation, gp_kernel
+        self.priors, self.hyperpriors = priors, hyperpriors
+        self.fixed_params, self.fixed_hyperparams = fixed_params, fixed_hyperparams
+        self.free_params_names, self.free_hyperparams_names = free_params_names, free_hyperparams_names
+        self.time, self.vel, self.velerr, self.t0 = time, vel, velerr, t0
+        self.instrument, self.unique_instruments = instrument, unique_instruments
+        self.gp_log_likelihood = GPLogLikelihood(time, vel, velerr, t0, instrument, unique_instruments,
+                                                 planet_letters, parameterisation, gp_kernel)
+        self.log_prior = LogPrior(self.priors)
+        self.log_hyperprior = LogPrior(self.hyperpriors)
+        (self._logprob_jacobian_correction, self._logprob_prior_renorm_correction,
+         self._logprob_correction_breakdown) = compute_logprob_corrections(
+            planet_letters, _par_str(parameterisation), priors, free_params_names)
+
+    def _make_descriptor(self) -> Descriptor:
+        return Descriptor(self.planet_letters, _par_str(self.parameterisation), self.priors, self.fixed_params,
+                          self.free_params_names, self.unique_instruments, self.t0,
+                          hyperpriors=self.hyperpriors, fixed_hyperparams=self.fixed_hyperparams,
+                          free_hyperparams_names=self.free_hyperparams_names,
+                          jacobian=self._logprob_jacobian_correction,
+                          renorm=self._logprob_prior_renorm_correction)
+
+    def log_probability_batch(self, theta):
+        return self._eval_batch(theta)
+
+    def log_probability(self, combined: Dict[str, float]) -> float:
+        """fit.py:7836-7901."""
+        names = list(self.free_params_names) + list(self.free_hyperparams_names)
+        row = np.array([[float(combined[n]) for n in names]])
+        return float(self.ctx.logprob_host(row)[0])
+
+    def _negative_log_probability_for_MAP(self, vals) -> float:
+        """fit.py:7903-7939."""
+        neg = -float(self.ctx.logprob_host(np.asarray(vals, dtype=np.float64).reshape(1, -1))[0])
+        return 1e30 if not np.isfinite(neg) else neg
+
+
+def from_spec(spec: dict):
+    """Build a LogPosterior / GPLogPosterior from a workload spec (ravest_b200/workloads.py)."""
+    from . import prior as P
+    params = spec["params"]
+    free = [k for k, (_, fx) in params.items() if not fx]
+    fixed = {k: v for k, (v, fx) in params.items() if fx}
+    priors = {k: P.from_tuple(v) for k, v in spec["priors"].items()}
+    inst = np.asarray(spec["instrument"])
+    args = dict(time=np.ascontiguousarray(spec["time"], dtype=np.float64),
+                vel=np.ascontiguousarray(spec["vel"], dtype=np.float64),
+                velerr=np.ascontiguousarray(spec["velerr"], dtype=np.float64),
+                instrument=inst, unique_instruments=np.unique(inst), t0=spec["t0"])
+    par = Parameterisation(spec["parameterisation"])
+    if "hyperparams" in spec:
+        hp = spec["hyperparams"]
+        return GPLogPosterior(list(spec["planet_letters"]), par, GPKernel("Quasiperiodic"), priors,
+                              {k: P.from_tuple(v) for k, v in spec["hyperpriors"].items()}, fixed,
+                              {k: v for k, (v, fx) in hp.items() if fx}, free,
+                              [k for k, (_, fx) in hp.items() if not fx], **args)
+    return LogPosterior(list(spec["planet_letters"]), par, priors, fixed, free, **args)

@@ -1,0 +1,336 @@
+"""Parity of the CUDA path (through the C ABI) with the reference's golden vectors and the oracle."""
+import pickle
+
+import numpy as np
+import pytest
+
+from conftest import assert_logp_close, assert_rv_close, load_golden, spec_from_json
+
+pytestmark = pytest.mark.gpu
+
+
+def _post(spec):
+    from ravest_b200 import fit
+    return fit.from_spec(spec)
+
+
+# ------------------------------------------------------------------ model.py goldens
+def test_rv_golden_vectors(cuda):
+    from ravest_b200 import model, param
+    g = load_golden("rv")
+    for c in g["planet_cases"]:
+        pl = model.Planet("b", param.Parameterisation(c["parameterisation"]), c["params"])
+        rv = pl.radial_velocity(np.array(c["t"]))
+        e = c["params"].get("e", 0.37)
+        # conditioning: e >= 0.99 amplifies ulp(M) by 1/(1-e)^2 in BOTH implementations
+        rtol = 1e-9 if e <= 0.97 else (1e-8 if e <= 0.99 else 1e-6)
+        assert_rv_close(rv, c["rv"], c["params"]["K"], c["name"], rtol=rtol)
+    for c in g["planet_cases"][:2]:                      # the reference's own rv1.txt / rv2.txt
+        pl = model.Planet("b", param.Parameterisation("P K e w Tp"), c["params"])
+        assert np.abs(pl.radial_velocity(np.array(c["t"])) - np.array(c["rv"])).max() < 1e-12
+
+
+def test_bare_kernel_and_circular_dispatch(cuda):
+    from ravest_b200 import model
+    g = load_golden("rv")
+    for c in g["kernel_cases"]:
+        rv = model._njit_kepler_rv(np.array(c["M"]), c["e"], c["K"], c["w"])
+        assert_rv_close(rv, c["rv"], c["K"], f"kernel e={c['e']}")
+    M = np.linspace(-20, 20, 501)
+    assert np.abs(model._compute_rv(M, 0.0, 3.0, 0.4) - 3.0 * np.cos(M + 0.4)).max() < 1e-14   # test_model.py:306-314
+    t = cuda.as_tensor(M, device="cuda")
+    assert isinstance(model._compute_rv(t, 0.3, 1.0, 0.0), cuda.Tensor)
+
+
+def test_star_is_sum_of_planets_plus_trend(cuda):
+    from ravest_b200 import model, param
+    c = load_golden("rv")["star_case"]
+    star = model.Star("s", 1.0)
+    P = param.Parameterisation("P K e w Tp")
+    for L, pp in c["planets"]:
+        star.add_planet(model.Planet(L, P, pp))
+    star.add_trend(model.Trend(t0=c["trend"]["t0"], params={"gd": c["trend"]["gd"], "gdd": c["trend"]["gdd"]}))
+    assert np.abs(star.radial_velocity(np.array(c["t"])) - np.array(c["rv"])).max() < 1e-12
+
+
+def test_planet_constructor_errors(cuda):
+    from ravest_b200 import model, param
+    P = param.Parameterisation("P K e w Tp")
+    ok = {"P": 3.0, "K": 2.0, "e": 0.1, "w": 0.2, "Tp": 0.0}
+    for bad in ({"P": 0.0}, {"P": -1.0}, {"K": 0.0}, {"e": -0.1}, {"e": 1.0}, {"w": np.pi}, {"w": -3.5}):
+        with pytest.raises(ValueError):
+            model.Planet("b", P, ok | bad)
+    model.Planet("b", P, ok | {"w": -np.pi})
+    with pytest.raises(ValueError):
+        model.Planet("bc", P, ok)
+    with pytest.raises(ValueError):
+        model.Planet("b", param.Parameterisation("P K e w Tc"), ok)
+    with pytest.raises(ValueError):
+        model.Planet("b", param.Parameterisation("P K secosw sesinw Tc"),
+                     {"P": 3.0, "K": 1.0, "secosw": 0.9, "sesinw": 0.9, "Tc": 0.0})
+
+
+def test_tc_tp_and_uv_conversions(cuda):
+    from ravest_b200 import param
+    g = load_golden("tctp")
+    rows = g["tc_to_tp"]
+    Pz = param.Parameterisation("P K e w Tc")
+    out, valid = Pz.convert_batch([[r["P"], 1.0, r["e"], r["w"], r["Tc"]] for r in rows])
+    ref = np.array([r["Tp"] for r in rows])
+    assert np.abs(out[:, 4].cpu().numpy() - ref).max() < 1e-11
+    for r in rows[:4]:                                   # tests/test_param.py:82-91 known answers
+        d = Pz.convert_pars_to_default_parameterisation({"P": r["P"], "K": 1.0, "e": r["e"], "w": r["w"], "Tc": r["Tc"]})
+        assert np.isclose(d["Tp"], r["published_Tp"], rtol=1e-14, atol=1e-14)
+    uv = g["uv_to_ew"]
+    Pu = param.Parameterisation("P K secosw sesinw Tp")
+    out, valid = Pu.convert_batch([[3.0, 1.0, r["secosw"], r["sesinw"], 0.0] for r in uv])
+    assert np.array_equal(out[:, 2].cpu().numpy(), np.array([r["e"] for r in uv]))
+    assert np.abs(out[:, 3].cpu().numpy() - np.array([r["w"] for r in uv])).max() < 1e-15
+    v = dict(zip([(r["secosw"], str(r["sesinw"])) for r in uv], valid.cpu().numpy()))
+    assert v[(-0.5, "0.0")] == 0 and v[(-0.5, "-0.0")] == 1 and v[(1.0, "0.0")] == 0
+    with pytest.raises(ValueError):
+        Pz.convert_pars_to_default_parameterisation({"P": 3.0, "K": 1.0, "e": 1.2, "w": 0.0, "Tc": 0.0})
+
+
+def test_priors_against_reference_table(cuda):
+    from ravest_b200 import prior as P
+    for c in load_golden("priors"):
+        obj = P.from_tuple(c["prior"])
+        got = obj.logpdf_batch(np.array(c["x"]))
+        ref = np.array(c["logp"])
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), c["prior"]
+        assert np.array_equal(np.isinf(got), np.isinf(ref)), c["prior"]
+        inf = np.isinf(ref)
+        assert np.array_equal(got[inf], ref[inf]), c["prior"]
+        fin = np.isfinite(ref)
+        assert np.all(np.abs(got[fin] - ref[fin]) <= 5e-13 * np.maximum(1.0, np.abs(ref[fin]))), c["prior"]
+    assert P.Uniform(0, 2)(1.0) == -np.log(2.0) and P.Rayleigh(1.0)(0.0) == -np.inf     # scalar call convention
+
+
+# ------------------------------------------------------------------ fit.py goldens
+def test_notebook_known_answers(cuda):
+    for c in load_golden("known_answers"):
+        post = _post(spec_from_json(c["spec"]))
+        theta = np.array(c["theta"])
+        got = post.log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
+        assert_logp_close(got, c["logprob"], c["name"])
+        # scalar conventions of the reference: dict in, float out; MAP wrapper
+        x = dict(zip(c["free_names"], theta[0]))
+        assert abs(post.log_probability(x) + c["map_fun"]) < 1e-7
+        assert abs(post._negative_log_probability_for_MAP(list(theta[0])) - c["map_fun"]) < 1e-7
+    ka1 = load_golden("known_answers")[0]
+    assert abs(ka1["map_fun"] - 794.802645093951) == 0.0           # example_fitting.ipynb:352
+
+
+def test_logprob_cases_all_parameterisations_priors_edges(cuda):
+    for c in load_golden("logprob_cases"):
+        spec = spec_from_json(c["spec"])
+        post = _post(spec)
+        theta = np.array(c["theta"])
+        got = post.log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
+        assert_logp_close(got, c["logprob"], c["name"])
+        ll, lp = post.log_probability_parts_batch(theta)
+        assert_logp_close(ll.cpu().numpy(), c["loglike"], c["name"] + " loglike")
+        ref_lp = np.array([np.nan if v is None else v for v in c["logprior"]], dtype=float)
+        ok = np.isfinite(ref_lp)
+        assert np.abs(lp.cpu().numpy()[ok] - ref_lp[ok]).max() < 1e-9, c["name"]
+        assert abs(post._logprob_jacobian_correction - c["jacobian"]) < 1e-15
+        assert abs(post._logprob_prior_renorm_correction - c["renorm"]) < 1e-15
+        # full-parameter LogLikelihood.__call__ (fit.py:3600-3660): dict of ALL params
+        i = int(np.flatnonzero(np.isfinite(c["loglike"]))[0])
+        fixed = {k: v for k, (v, fx) in spec["params"].items() if fx}
+        full = fixed | dict(zip(c["free_names"], theta[i]))
+        assert abs(post.log_likelihood(full) - c["loglike"][i]) <= 1e-7 + 2e-13 * abs(c["loglike"][i])
+        bad = dict(full)
+        bad["K_b"] = -1.0
+        assert post.log_likelihood(bad) == -np.inf                   # tests/test_fit.py:381-487
+
+
+def test_rv_matrix_mode(cuda):
+    for c in load_golden("rv_matrix"):
+        spec = spec_from_json(c["spec"])
+        post = _post(spec)
+        theta, times = np.array(c["theta"]), np.array(c["times"])
+        for k, L in enumerate(spec["planet_letters"]):
+            got = post.ctx.rv_matrix(theta, times, k).cpu().numpy()
+            assert np.abs(got - np.array(c["components"][L])).max() < 1e-9 * 25
+        assert np.abs(post.ctx.rv_matrix(theta, times, -1).cpu().numpy() - np.array(c["components"]["trend"])).max() < 1e-12
+        assert np.abs(post.ctx.rv_matrix(theta, times, -2).cpu().numpy() - np.array(c["components"]["total"])).max() < 1e-9 * 25
+        bad = theta.copy()
+        bad[0, c["free_names"].index("K_b")] = -1.0
+        out = post.ctx.rv_matrix(bad, times, -2).cpu().numpy()
+        assert np.isnan(out[0]).all() and np.isfinite(out[1:]).all()
+
+
+# ------------------------------------------------------------------ oracle on seeded workloads
+@pytest.mark.parametrize("name,S", [("c1", 512), ("c1c", 512), ("c2", 4096), ("c3", 1024), ("c4", 1024)])
+def test_workloads_against_c_oracle(cuda, name, S):
+    from oracle import oracle_c
+    from ravest_b200 import workloads
+    make = {"c1": lambda: workloads.make_c1(S), "c1c": lambda: workloads.make_c1(S, circular=True),
+            "c2": lambda: workloads.make_c2(S), "c3": lambda: workloads.make_c3(S), "c4": lambda: workloads.make_c4(S)}
+    spec, theta = make[name]()
+    post = _post(spec)
+    got = post.log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
+    ref = oracle_c.OracleProblem(spec).logprob(theta)
+    assert np.isneginf(ref).sum() >= 1 and np.isfinite(ref).sum() > S // 2
+    assert_logp_close(got, ref, name)
+    # RV matrix against the oracle, |d| <= 1e-9 max(|rv|, K)
+    times = np.asarray(spec["time"])[:97]
+    orc = oracle_c.OracleProblem(spec)
+    sub = theta[np.isfinite(ref)][:64]
+    for k in range(len(spec["planet_letters"])):
+        a = post.ctx.rv_matrix(sub, times, k).cpu().numpy()
+        b = orc.rv_matrix(sub, times, k)
+        K = sub[:, post.free_params_names.index(f"K_{spec['planet_letters'][k]}")][:, None]
+        assert (np.abs(a - b) <= 1e-9 * np.maximum(np.abs(b), K)).all(), (name, k)
+
+
+def test_high_eccentricity_extremes(cuda):
+    """e up to 0.9999 incl. epochs at periastron: compare in units of the problem's own conditioning."""
+    from oracle import oracle_c
+    from ravest_b200 import model
+    rng = np.random.default_rng(3)
+    for e in (0.9, 0.97, 0.99, 0.995, 0.999, 0.9995, 0.9999):
+        M = np.concatenate([rng.uniform(-40, 40, 4000), 2 * np.pi * np.arange(-3, 4) + 1e-9,
+                            10.0 ** rng.uniform(-12, -1, 500), [0.0, np.pi, -np.pi]])
+        got = model._njit_kepler_rv(M, e, 1.0, 0.7)
+        ref = oracle_c.kepler_rv(M, e, 1.0, 0.7)
+        # |dE| ~ ulp(M) / (1 - e cos E) and d(rv)/dE <~ 1/(1 - e): bound by 4e-15 / (1 - e)^2 + 1e-13
+        assert np.abs(got - ref).max() <= 4e-15 * 41 / (1 - e) ** 2 + 1e-13, e
+
+
+# ------------------------------------------------------------------ properties at full size
+def test_bit_stability_under_sharding_and_batching(cuda):
+    from ravest_b200 import dist, workloads
+    spec, theta = workloads.make_c3(n_samples=20_000)
+    post = _post(spec)
+    th = cuda.as_tensor(theta, device="cuda")
+    full = post.log_probability_batch(th)
+    for world in (2, 3, 8):
+        parts = [post.log_probability_batch(th[lo:hi]) for lo, hi in
+                 (dist.shard_bounds(len(theta), world, r) for r in range(world))]
+        assert cuda.equal(cuda.cat(parts).view(cuda.int64), full.view(cuda.int64)), world
+    odd = cuda.cat([post.log_probability_batch(th[:7]), post.log_probability_batch(th[7:10_001]),
+                    post.log_probability_batch(th[10_001:])])
+    assert cuda.equal(odd.view(cuda.int64), full.view(cuda.int64))      # not even batch-aligned
+    perm = cuda.randperm(len(theta), device="cuda")
+    assert cuda.equal(post.log_probability_batch(th[perm]).view(cuda.int64), full[perm].view(cuda.int64))
+    host = post.log_probability_batch(theta)                            # NumPy through the host-buffer ABI
+    assert np.array_equal(host.view(np.int64), full.cpu().numpy().view(np.int64))
+
+
+def test_full_size_c3_properties(cuda):
+    """BASELINE config 3 at full size (1e6 x 1000 x 5): invariants + an oracle-checked subsample."""
+    from oracle import oracle_c
+    from ravest_b200 import workloads
+    spec, theta = workloads.make_c3(n_samples=1_000_000)
+    post = _post(spec)
+    th = cuda.as_tensor(theta, device="cuda")
+    out = post.log_probability_batch(th).cpu().numpy()
+    n_inf = int(np.isneginf(out).sum())
+    assert 500 <= n_inf <= 20_000 and not np.isnan(out).any()
+    idx = np.random.default_rng(0).choice(len(theta), 1500, replace=False)
+    ref = oracle_c.OracleProblem(spec).logprob(theta[idx])
+    assert_logp_close(out[idx], ref, "c3 subsample")
+    # the likelihood is invariant under relabelling the planets (same physical model)
+    names = post.free_params_names
+    swap = theta[idx].copy()
+    for p in ("P", "K", "secosw", "sesinw", "Tc"):
+        i, j = names.index(f"{p}_b"), names.index(f"{p}_e")
+        swap[:, [i, j]] = swap[:, [j, i]]
+    ll0, _ = post.log_probability_parts_batch(theta[idx])
+    ll1, _ = post.log_probability_parts_batch(swap)
+    a, b = ll0.cpu().numpy(), ll1.cpu().numpy()
+    ok = np.isfinite(a) & np.isfinite(b)
+    assert np.abs(a[ok] - b[ok]).max() <= 1e-9 * np.abs(a[ok]).max()
+
+
+def test_full_size_c4_high_e(cuda):
+    from oracle import oracle_c
+    from ravest_b200 import workloads
+    spec, theta = workloads.make_c4(n_samples=200_000)
+    post = _post(spec)
+    out = post.log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
+    idx = np.random.default_rng(1).choice(len(theta), 1500, replace=False)
+    assert_logp_close(out[idx], oracle_c.OracleProblem(spec).logprob(theta[idx]), "c4 subsample")
+
+
+# ------------------------------------------------------------------ shapes, edges, plumbing
+def test_ragged_and_tiny_shapes(cuda):
+    from oracle import oracle_c
+    from ravest_b200 import workloads
+    for n_epochs in (1, 2, 31, 32, 33, 63, 64, 65, 127, 129, 1000, 1025):
+        spec, theta = workloads.make_multiplanet(2, n_epochs, 37, seed=n_epochs, instruments=("A", "B"),
+                                                 t_span=50.0 + n_epochs, invalid_frac=0.05)
+        post = _post(spec)
+        got = post.log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
+        assert_logp_close(got, oracle_c.OracleProblem(spec).logprob(theta), f"N={n_epochs}")
+    spec, theta = workloads.make_c2(64)
+    post = _post(spec)
+    th = cuda.as_tensor(theta, device="cuda")
+    assert post.log_probability_batch(th[:0]).shape == (0,)
+    one = post.log_probability_batch(th[:1])
+    assert one.shape == (1,) and cuda.equal(one, post.log_probability_batch(th)[:1])
+    with pytest.raises(ValueError):
+        post.log_probability_batch(th[:, :-1])
+
+
+def test_too_many_epochs_is_a_clean_error(cuda):
+    from ravest_b200 import _lib, workloads
+    spec, theta = workloads.make_multiplanet(1, 9000, 4, seed=2, t_span=9000.0)
+    with pytest.raises(_lib.RvlpError):
+        _post(spec).log_probability_batch(theta)
+
+
+def test_nan_rows_follow_reference(cuda):
+    from oracle import oracle_py
+    from ravest_b200 import workloads
+    spec, theta = workloads.make_multiplanet(2, 40, 16, seed=4, parameterisation="P K e w Tp", invalid_frac=0.0,
+                                             prior_style="uniform")
+    names = workloads.free_names(spec)
+    theta[1, names.index("K_b")] = np.nan          # Uniform prior: NaN passes every comparison -> NaN
+    theta[2, names.index("gd")] = np.nan           # Normal prior: lp = NaN -> -inf (fit.py:3481)
+    theta[3, names.index("P_c")] = np.nan
+    theta[3, names.index("K_b")] = -1.0            # invalid planet wins over NaN elsewhere
+    ref = oracle_py.Problem(spec).log_probability_batch(theta)
+    got = _post(spec).log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
+    assert np.isnan(ref[1]) and ref[2] == -np.inf and ref[3] == -np.inf
+    assert_logp_close(got, ref, "nan rows")
+
+
+def test_pickle_roundtrip_and_emcee_vectorize_contract(cuda):
+    from ravest_b200 import workloads
+    spec, theta = workloads.make_c2(256)
+    post = _post(spec)
+    a = post.log_probability_batch(theta)
+    clone = pickle.loads(pickle.dumps(post))       # multiprocessing=True pickles LogPosterior (fit.py:1069-1072)
+    assert np.array_equal(clone.log_probability_batch(theta), a, equal_nan=True)
+    # emcee vectorize=True: f(coords[n, ndim]) -> n values, NumPy in / NumPy out
+    assert isinstance(a, np.ndarray) and a.shape == (256,) and a.dtype == np.float64
+
+
+def test_gp_against_restatement(cuda):
+    """Config 5. GP parity is unpinned against tinygp (absent); the CUDA kernel is held to the
+    C / numpy restatements of SURVEY.md Appendix A.5."""
+    from oracle import oracle_c, oracle_py
+    from ravest_b200 import workloads
+    for n_pl, N in ((1, 120), (2, 57)):
+        spec, theta = workloads.make_c5(n_samples=300, n_planets=n_pl, n_epochs=N)
+        post = _post(spec)
+        got = post.log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
+        ref = oracle_c.OracleProblem(spec).logprob(theta)
+        assert np.array_equal(np.isneginf(got), np.isneginf(ref)) and np.isneginf(ref).any()
+        fin = np.isfinite(ref)
+        assert np.all(np.abs(got[fin] - ref[fin]) <= 1e-7 + 1e-11 * np.abs(ref[fin]))
+        py = oracle_py.Problem(spec).gp_log_probability_batch(theta[:20])
+        f2 = np.isfinite(py)
+        assert np.all(np.abs(got[:20][f2] - py[f2]) <= 1e-7 + 1e-11 * np.abs(py[f2]))
+    x = dict(zip(post.free_params_names + post.free_hyperparams_names, theta[5]))
+    assert abs(post.log_probability(x) - got[5]) == 0.0
+
+
+def test_fp64_peak_probe(cuda):
+    from ravest_b200 import _lib
+    flops, ms = _lib.measure_fp64_peak(0, 2048)
+    assert 5e12 < flops < 8e13, flops
