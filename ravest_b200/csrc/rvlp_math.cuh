@@ -313,7 +313,16 @@ RV_HD DefaultPars to_default(int par, const double* in) {
     d.e = in[2];
     d.w = in[3];
   } else {
-    d.e = in[2] * in[2] + in[3] * in[3];   // param.py:232
+    // param.py:232 — secosw**2 + sesinw**2 with numpy's three roundings (no FMA contraction): the
+    // validity tests compare e with 0 and 1 exactly
+#if defined(__CUDA_ARCH__)
+    d.e = __dadd_rn(__dmul_rn(in[2], in[2]), __dmul_rn(in[3], in[3]));
+#else
+    {
+      volatile double uu = in[2] * in[2], vv = in[3] * in[3];
+      d.e = uu + vv;
+    }
+#endif
     d.w = atan2(in[3], in[2]);             // param.py:233
   }
   if (par == RVLP_PAR_PKEWTC || par == RVLP_PAR_PKSECTC) {
