@@ -17,7 +17,8 @@ from .descriptor import DescPOD, PriorPOD, make_prior_pod
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libravest_b200.so")
+# RVLP_LIB lets tools/kernel_sweep.py time alternative builds of the same sources; it is not a fallback
+LIB_PATH = os.environ.get("RVLP_LIB") or os.path.join(CSRC, "libravest_b200.so")
 SOURCES = ["rvlp_capi.cu"]
 HEADERS = ["rvlp_math.cuh", "rvlp_kernels.cuh", "rvlp_gp.cuh", os.path.join("..", "..", "include", "ravest_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -18,9 +18,15 @@
 
 namespace rvlp {
 
+#ifndef RVLP_W
+#define RVLP_W 4
+#endif
+#ifndef RVLP_MIN_BLOCKS
+#define RVLP_MIN_BLOCKS 2
+#endif
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kW = 2;             // epochs per lane in flight
+constexpr int kW = RVLP_W;        // epochs per lane in flight (ILP)
 constexpr int kG = 4;             // samples whose prologue a warp does together
 constexpr int kPlanetRec = 16;    // doubles per planet in the sample record
 constexpr double kLog2Pi = 1.8378770664093453;   // np.log(2*np.pi), fit.py:3595
@@ -39,7 +45,7 @@ constexpr int kHdr = 6;           // sample record header doubles
 __host__ __device__ inline int sample_rec_doubles(int n_planets, int n_inst) {
   return kHdr + 2 * n_inst + kPlanetRec * n_planets;
 }
-// sample record: [0] lp  [1] flags  [2] gd  [3] gdd  [4] lhp  [5] -  [6..) gamma[n_inst]  jit2[n_inst]  planets
+// sample record: [0] lp  [1] flags  [2] gd  [3] gdd  [4] lhp  [5] sum_k C_k  [6..) gamma[n_inst]  jit2[n_inst]  planets
 // planet record: n tp e A B C w K | tol plan(bits) P Kraw e w tp invalid
 enum { F_JIT = 1, F_PLANET = 2, F_PRIOR = 4, F_HYPER = 8, F_SKIP = 16 };
 
@@ -195,8 +201,12 @@ __device__ __forceinline__ void sample_prologue(const DevProblem& P, const Table
       sr[kHdr + P.n_inst + j] = jit * jit;                     // fit.py:3654
     }
     const double* planets = sr + kHdr + 2 * P.n_inst;
-    for (int k = 0; k < npl; ++k)
+    double csum = 0.0;
+    for (int k = 0; k < npl; ++k) {
       if (planets[k * kPlanetRec + 15] != 0.0) flags |= F_PLANET;
+      csum += planets[k * kPlanetRec + 5];                  // K e cos w of every planet (model.py:170)
+    }
+    sr[5] = csum;
     if (P.n_hyper) {                                        // gp.py:98-108
       for (int k = 0; k < 4; ++k) {
         const double h = model_param(T, row, P.n_model + k);
@@ -228,39 +238,35 @@ __device__ __forceinline__ void sample_prologue(const DevProblem& P, const Table
 template <int W>
 __device__ __forceinline__ void model_rv(const DevProblem& P, const double* sr, const double (&tt)[W],
                                          double (&rv)[W], int only_planet, bool with_trend) {
-  const double* planets = sr + kHdr + 2 * P.n_inst;
+  const double2* planets = reinterpret_cast<const double2*>(sr + kHdr + 2 * P.n_inst);
+  const double c0 = only_planet < 0 ? sr[5]
+                                    : (only_planet < P.n_planets ? sr[kHdr + 2 * P.n_inst + only_planet * kPlanetRec + 5] : 0.0);
 #pragma unroll
-  for (int j = 0; j < W; ++j) rv[j] = 0.0;
+  for (int j = 0; j < W; ++j) rv[j] = c0;
   for (int k = 0; k < P.n_planets; ++k) {
     if (only_planet >= 0 && k != only_planet) continue;
-    const double* pr = planets + k * kPlanetRec;
+    const double2* pr = planets + k * (kPlanetRec / 2);     // 16-byte aligned: LDS.128 broadcasts
+    const double2 a = pr[0], b = pr[1], c = pr[2], d = pr[3], e = pr[4];
     PlanetConst pc;
-    pc.n = pr[0]; pc.tp = pr[1]; pc.e = pr[2]; pc.A = pr[3]; pc.B = pr[4]; pc.C = pr[5];
-    pc.w = pr[6]; pc.K = pr[7];
+    pc.n = a.x; pc.tp = a.y; pc.e = b.x; pc.A = b.y; pc.B = c.x; pc.C = c.y; pc.w = d.x; pc.K = d.y;
     SolverPlan plan;
-    plan.tol = pr[8];
-    plan.n32 = __double2loint(pr[9]);
-    plan.n64 = __double2hiint(pr[9]);
-    double r[W];
-    planet_rv<W>(pc, plan, tt, r);
-#pragma unroll
-    for (int j = 0; j < W; ++j) rv[j] += r[j];
+    plan.tol = e.x;
+    plan.n32 = __double2loint(e.y);
+    plan.n64 = __double2hiint(e.y);
+    planet_rv_add<W>(pc, plan, tt, rv);
   }
   if (with_trend) {                                          // model.py:483-509
     const double gd = sr[2], gdd = sr[3];
 #pragma unroll
     for (int j = 0; j < W; ++j) {
       const double dt = tt[j] - P.t0;
-      double tr = 0.0;
-      if (gd != 0) tr += gd * dt;
-      if (gdd != 0) tr += gdd * (dt * dt);
-      rv[j] += tr;
+      rv[j] = fma(gdd, dt * dt, fma(gd, dt, rv[j]));         // exact zeros when gd / gdd == 0
     }
   }
 }
 
 // ------------------------------------------------------------------ K1: log-probability
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, RVLP_MIN_BLOCKS)
 logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double* __restrict__ out,
                double* __restrict__ ll_out, double* __restrict__ lp_out) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -288,7 +294,11 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
       } else if ((flags & (F_JIT | F_PRIOR)) && ll_out == nullptr) {
         ll = 0.0;                                            // result is -inf regardless: skip the work
       } else {
-        double acc = 0.0;
+        // Lane partials in fixed epoch order: chi^2 sum, product of the variances' mantissas and
+        // sum of their exponents (sum_i ln var_i = ln prod mant_i + ln2 sum ex_i: one log per lane
+        // per sample instead of one per epoch).
+        double chi = 0.0, prodm = 1.0, slow = 0.0;
+        int exsum = 0, cnt = 0;
         for (int base = 0; base < P.n_pad; base += 32 * kW) {
           double tt[kW], rv[kW];
           int idx[kW];
@@ -298,16 +308,35 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
             tt[j] = T.t[idx[j]];
           }
           model_rv<kW>(P, sr, tt, rv, -1, true);
+          double var[kW], res[kW];
+          bool odd = false;
 #pragma unroll
           for (int j = 0; j < kW; ++j) {
             const int in = T.inst[idx[j]];
             const double tot = rv[j] + sr[kHdr + in];           // fit.py:3642-3644
-            const double var = T.e2[idx[j]] + sr[kHdr + P.n_inst + in];
-            const double res = tot - T.v[idx[j]];
-            const double term = res * res / var + (kLog2Pi + log(var));   // fit.py:3655-3658
-            if (idx[j] < P.n_epochs) acc += term;
+            var[j] = T.e2[idx[j]] + sr[kHdr + P.n_inst + in];   // fit.py:3654
+            res[j] = tot - T.v[idx[j]];
+            const int h = __double2hiint(var[j]);
+            const bool normal = (unsigned)(h - 0x00100000) < 0x7fe00000u;   // positive, normal, finite
+            const bool live = idx[j] < P.n_epochs;
+            odd |= live && !normal;
+            if (live && normal) {                               // fit.py:3655-3658
+              chi = fma(res[j] * res[j], rcp64(var[j]), chi);
+              prodm *= __hiloint2double((h & 0x000fffff) | 0x3ff00000, __double2loint(var[j]));
+              exsum += (h >> 20) - 1023;
+              cnt += 1;
+            }
+          }
+          if (__any_sync(0xffffffffu, odd)) {                   // var == 0, denormal, inf, NaN: IEEE path
+#pragma unroll
+            for (int j = 0; j < kW; ++j) {
+              const int h = __double2hiint(var[j]);
+              if (idx[j] < P.n_epochs && !((unsigned)(h - 0x00100000) < 0x7fe00000u))
+                slow += res[j] * res[j] / var[j] + (kLog2Pi + log(var[j]));
+            }
           }
         }
+        double acc = chi + ((double)cnt * kLog2Pi + fma((double)exsum, 0.6931471805599453, log(prodm))) + slow;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         ll = -0.5 * acc;
@@ -331,7 +360,7 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
 }
 
 // ------------------------------------------------------------------ K2: RV matrix (fit.py:2690-2824)
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, RVLP_MIN_BLOCKS)
 rv_matrix_kernel(DevProblem P, const double* __restrict__ theta, int64_t S,
                  const double* __restrict__ times, int64_t T_n, int component, double* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -392,8 +421,8 @@ __global__ void kepler_rv_kernel(const double* __restrict__ M, int64_t n, double
   const SolverPlan plan = plan_for(e);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    double tt[1] = {M[i]}, r[1];
-    planet_rv<1>(pc, plan, tt, r);
+    double tt[1] = {M[i]}, r[1] = {pc.C};
+    planet_rv_add<1>(pc, plan, tt, r);
     rv[i] = r[0];
   }
 }
@@ -406,8 +435,8 @@ __global__ void planet_rv_kernel(DefaultPars d, const double* __restrict__ t, in
   const SolverPlan plan = plan_for(d.e);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    double tt[1] = {t[i]}, r[1];
-    planet_rv<1>(pc, plan, tt, r);
+    double tt[1] = {t[i]}, r[1] = {pc.C};
+    planet_rv_add<1>(pc, plan, tt, r);
     rv[i] = accumulate ? rv[i] + r[0] : r[0];
   }
 }

@@ -11,6 +11,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/ravest_b200.h"
 
@@ -38,10 +39,68 @@ constexpr double BIG_M = 6.0e6;                    // |M| beyond this takes the 
 RV_HD double ffma(double a, double b, double c) { return ::fma(a, b, c); }
 RV_HD float ffmaf(float a, float b, float c) { return ::fmaf(a, b, c); }
 
+// ---------------------------------------------------------------- bit helpers
+RV_HD int hi32(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double2hiint(x);
+#else
+  int64_t b;
+  memcpy(&b, &x, 8);
+  return (int)(b >> 32);
+#endif
+}
+RV_HD double xor_hi(double x, int mask) {   // flip bits of the high word (sign manipulation)
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(x) ^ mask, __double2loint(x));
+#else
+  int64_t b;
+  memcpy(&b, &x, 8);
+  b ^= ((int64_t)(uint32_t)mask) << 32;
+  memcpy(&x, &b, 8);
+  return x;
+#endif
+}
+RV_HD double from_hi(int hi) {              // double with the given high word and a zero low word
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(hi, 0);
+#else
+  int64_t b = ((int64_t)(uint32_t)hi) << 32;
+  double x;
+  memcpy(&x, &b, 8);
+  return x;
+#endif
+}
+#if defined(__CUDA_ARCH__)
+#define RV_ANY(pred) __any_sync(__activemask(), (pred))
+#else
+#define RV_ANY(pred) (pred)
+#endif
+
+// Polynomial coefficients live in constant memory on the device so that DFMA reads them as
+// c[bank][offset] operands (as immediates they cost two UMOVs per use: ~10% of all issue slots).
+#define RV_SINCOS_COEFS                                                                         \
+  { 1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,        \
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,       \
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,       \
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02,        \
+    /* 12: -pi/2 head, tail */ -1.5707963267341256, -6.077100506506192e-11,                     \
+    /* 14: 1/2pi, rint magic, -2pi split */ 0.15915494309189535, 6755399441055744.0,            \
+    -6.2831853069365025, -2.4308402025215864e-10, -8.089064995183803e-21,                       \
+    /* 19: 1/6, 1/24, -1/6 */ 1.0 / 6.0, 1.0 / 24.0, -1.0 / 6.0 }
+#if defined(__CUDACC__)
+__constant__ double kCoefDev[22] = RV_SINCOS_COEFS;
+#endif
+static const double kCoefHost[22] = RV_SINCOS_COEFS;
+#if defined(__CUDA_ARCH__)
+#define RVK(i) kCoefDev[i]
+#else
+#define RVK(i) kCoefHost[i]
+#endif
+
 // ---------------------------------------------------------------- reciprocals
 RV_HD double rcp64(double x) {
 #if defined(__CUDA_ARCH__)
-  // MUFU.RCP64H seed (~2^-20) + two Newton steps; x is never 0/inf/denormal at the call sites
+  // MUFU.RCP64H seed (~2^-20) + two Newton steps; x is a normal positive number at the call sites
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double e = ffma(-x, y, 1.0);
@@ -75,75 +134,73 @@ RV_HD float rsqrt32(float x) {
 }
 
 // ---------------------------------------------------------------- fp32 sin/cos on [0, pi]
-// x = E - pi/2 in [-pi/2, pi/2]:  sin E = cos x,  cos E = -sin x.  Degree 9 / 8 near-minimax
-// fits (abs error ~1e-7): the fp32 stage only has to deliver a starter good to ~1e-5.
+// The fp32 stage only has to deliver a starter good to ~1e-5: on the device the MUFU
+// approximations (abs error ~4e-7 on [0, pi]) are enough and cost two issue slots each.
 RV_HD void sincos_0pi_f32(float E, float& s, float& c) {
-  const float x = E - 1.57079632679f;
-  const float z = x * x;
-  float ps = ffmaf(2.630042900e-06f, z, -1.982125978e-04f);
-  ps = ffmaf(ps, z, 8.333231322e-03f);
-  ps = ffmaf(ps, z, -1.666666567e-01f);
-  float pc = ffmaf(2.342478365e-05f, z, -1.386700082e-03f);
-  pc = ffmaf(pc, z, 4.166554660e-02f);
-  pc = ffmaf(pc, z, -4.999999106e-01f);
-  const float sx = ffmaf(x * z, ps, x);
-  const float cx = ffmaf(z, pc, 1.0f);
-  s = cx;
-  c = -sx;
+#if defined(__CUDA_ARCH__)
+  s = __sinf(E);
+  c = __cosf(E);
+#else
+  s = sinf(E);
+  c = cosf(E);
+#endif
 }
 
 // ---------------------------------------------------------------- fp64 sin/cos kernels
 // |r| <= pi/4 (+ slack): the classic degree-13 / degree-14 minimax kernels (fdlibm constants).
 RV_HD void sincos_kernel(double r, double& s, double& c) {
   const double z = r * r;
-  double ps = ffma(1.58969099521155010221e-10, z, -2.50507602534068634195e-08);
-  ps = ffma(ps, z, 2.75573137070700676789e-06);
-  ps = ffma(ps, z, -1.98412698298579493134e-04);
-  ps = ffma(ps, z, 8.33333333332248946124e-03);
-  ps = ffma(ps, z, -1.66666666666666324348e-01);
-  double pc = ffma(-1.13596475577881948265e-11, z, 2.08757232129817482790e-09);
-  pc = ffma(pc, z, -2.75573143513906633035e-07);
-  pc = ffma(pc, z, 2.48015872894767294178e-05);
-  pc = ffma(pc, z, -1.38888888888741095749e-03);
-  pc = ffma(pc, z, 4.16666666666666019037e-02);
+  double ps = ffma(RVK(0), z, RVK(1));
+  ps = ffma(ps, z, RVK(2));
+  ps = ffma(ps, z, RVK(3));
+  ps = ffma(ps, z, RVK(4));
+  ps = ffma(ps, z, RVK(5));
+  double pc = ffma(RVK(6), z, RVK(7));
+  pc = ffma(pc, z, RVK(8));
+  pc = ffma(pc, z, RVK(9));
+  pc = ffma(pc, z, RVK(10));
+  pc = ffma(pc, z, RVK(11));
   s = ffma(r * z, ps, r);
   c = ffma(z, ffma(z, pc, -0.5), 1.0);
 }
 
 // sin/cos of x in [0, pi] (a hair outside is fine); xf is x rounded to fp32 and only picks
-// the quadrant, so any xf within ~1e-3 of x works.
+// the quadrant q in {0, 1, 2}, so any xf within ~1e-3 of x works.  r = x - q pi/2 by two FMAs
+// with q built from integer selects; the quadrant swap is two selects + two sign xors.
 RV_HD void sincos_0pi(double x, float xf, double& s, double& c) {
   const bool q1 = xf > 0.78539816f;
   const bool q2 = xf > 2.35619449f;
-  const double kh = q2 ? 2.0 * PIO2_H : (q1 ? PIO2_H : 0.0);
-  const double kl = q2 ? 2.0 * PIO2_L : (q1 ? PIO2_L : 0.0);
-  const double r = (x - kh) - kl;
+  const double qd = from_hi(q2 ? 0x40000000 : (q1 ? 0x3ff00000 : 0));   // 2.0 / 1.0 / 0.0
+  double r = ffma(qd, RVK(12), x);
+  r = ffma(qd, RVK(13), r);
   double sr, cr;
   sincos_kernel(r, sr, cr);
-  s = q2 ? -sr : (q1 ? cr : sr);
-  c = q2 ? -cr : (q1 ? -sr : cr);
+  const bool swap = q1 && !q2;
+  const double s0 = swap ? cr : sr;
+  const double c0 = swap ? sr : cr;
+  s = xor_hi(s0, q2 ? (int)0x80000000 : 0);
+  c = xor_hi(c0, q1 ? (int)0x80000000 : 0);
 }
 
-// Reduce a mean anomaly to m in [0, pi] and a sign:  M = 2 pi k + sg * m.
-// Three-term Cody-Waite; exact to ~1e-20 |k| for |M| < BIG_M.  Larger |M| (far outside any
-// real data set; the reference itself carries ulp(M) ~ 1e-9 rad of noise there) goes through
-// libm's exact reduction instead.
+// Reduce a mean anomaly to m in [0, pi] and a sign bit:  M = 2 pi k + sign * m.
+// Three-term Cody-Waite, exact to ~1e-20 |k| for |M| < BIG_M; larger |M| is flagged by the
+// caller (anomaly_is_big) and redone through libm's exact reduction (reduce_big).
 RV_SLOW double reduce_big(double M) {
   return atan2(sin(M), cos(M));   // NaN / inf propagate as NaN
 }
-
-RV_HD void reduce_anomaly(double M, double& m, bool& neg) {
-  double r;
-  if (fabs(M) < BIG_M) {
-    const double k = ffma(M, INV_2PI, RINT_MAGIC) - RINT_MAGIC;
-    r = ffma(-k, TWO_PI_1, M);
-    r = ffma(-k, TWO_PI_2, r);
-    r = ffma(-k, TWO_PI_3, r);
-  } else {
-    r = reduce_big(M);
-  }
-  neg = r < 0.0;
-  m = fabs(r);
+RV_HD bool anomaly_is_big(double M) {       // |M| >= BIG_M, inf or NaN, by an integer compare
+  return (hi32(M) & 0x7fffffff) >= 0x4156e360;   // high word of 6.0e6
+}
+RV_HD void split_sign(double r, double& m, int& sign) {
+  sign = hi32(r) & (int)0x80000000;
+  m = xor_hi(r, sign);
+}
+RV_HD void reduce_anomaly(double M, double& m, int& sign) {
+  const double k = ffma(M, RVK(14), RVK(15)) - RVK(15);
+  double r = ffma(k, RVK(16), M);
+  r = ffma(k, RVK(17), r);
+  r = ffma(k, RVK(18), r);
+  split_sign(r, m, sign);
 }
 
 // ---------------------------------------------------------------- Kepler solver
@@ -157,8 +214,9 @@ RV_HD void reduce_anomaly(double M, double& m, bool& neg) {
 //  3. fp64: ONE full sin/cos of E0, then n64 fourth-order (Householder-3) steps, each of
 //     which updates (sin E, cos E) by an angle-addition with a short series in the step
 //     instead of calling sin/cos again;
-//  4. `dlast` = |last step|: the caller checks it against the planet's tolerance and falls
-//     back to kepler_robust for the (rare) lanes that did not contract enough.
+//  4. `dlast` = last step: the caller checks |dlast| against the planet's tolerance (an
+//     integer compare that also catches NaN) and sends the (rare) lanes that did not
+//     contract enough, or whose |M| is huge, through kepler_robust.
 struct SolverPlan {
   int n32;       // fp32 Halley iterations
   int n64;       // fp64 Householder steps
@@ -181,26 +239,37 @@ RV_HD SolverPlan plan_for(double e) {
   return p;
 }
 
-template <int W>
+// true when the last step is too large (or NaN): compares the high words as integers
+RV_HD bool step_rejected(double dlast, double tol) {
+  return (hi32(dlast) & 0x7fffffff) >= hi32(tol) || hi32(tol) < 0;
+}
+
+// N32 / N64 >= 0 fix the iteration counts at compile time (straight-line code for the two plans
+// that cover e <= 0.97); -1 reads them from n32 / n64.
+template <int W, int N32 = -1, int N64 = -1>
 RV_HD void kepler_fast(const double (&M)[W], double e, int n32, int n64, double (&cosE)[W],
                        double (&sinE)[W], double (&dlast)[W]) {
+  if (N32 >= 0) n32 = N32;
+  if (N64 >= 0) n64 = N64;
   const float ef = (float)e;
   const float one_p_e2 = ffmaf(ef, ef, 1.0f);
   const float m2e = -2.0f * ef;
   double m[W];
-  bool neg[W];
+  int sign[W];
   float Ef[W], mf[W];
 #pragma unroll
   for (int i = 0; i < W; ++i) {
-    reduce_anomaly(M[i], m[i], neg[i]);
+    reduce_anomaly(M[i], m[i], sign[i]);
     mf[i] = (float)m[i];
     float s, c;
     sincos_0pi_f32(mf[i], s, c);
-    const float q = fmaxf(ffmaf(m2e, c, one_p_e2), 1e-12f);
+    // q = |1 - e exp(i m)|^2 >= (1 - e)^2 > 0; a rounding-negative q gives NaN, which the clamp at the
+    // end of the fp32 stage turns into E0 = 0 and the step test then rejects
+    const float q = ffmaf(m2e, c, one_p_e2);
     Ef[i] = ffmaf(ef * s, rsqrt32(q), mf[i]);
-    Ef[i] = fminf(Ef[i], 3.14159274f);
   }
-  for (int it = 0; it < n32; ++it) {
+#pragma unroll
+  for (int it = 0; it < (N32 >= 0 ? N32 : n32); ++it) {
 #pragma unroll
     for (int i = 0; i < W; ++i) {
       float s, c;
@@ -210,59 +279,61 @@ RV_HD void kepler_fast(const double (&M)[W], double e, int n32, int n64, double 
       const float fp = ffmaf(-ef, c, 1.0f);
       const float den = ffmaf(fp, fp, -0.5f * f * es);
       const float d = f * fp * rcp32(den);
-      Ef[i] = fminf(fmaxf(Ef[i] - d, 0.0f), 3.14159274f);
+      Ef[i] = Ef[i] - d;
     }
   }
   double E[W], s[W], c[W];
 #pragma unroll
   for (int i = 0; i < W; ++i) {
-    // NaN anomalies: keep them NaN (the reference returns NaN), comparisons above drop them
-    E[i] = (m[i] == m[i]) ? (double)Ef[i] : m[i];
+    Ef[i] = fminf(fmaxf(Ef[i], 0.0f), 3.14159274f);   // the fp64 kernels need E0 in [0, pi]; NaN -> 0
+    E[i] = (double)Ef[i];
     sincos_0pi(E[i], Ef[i], s[i], c[i]);
     dlast[i] = 0.0;
   }
-  for (int it = 0; it < n64; ++it) {
+#pragma unroll
+  for (int it = 0; it < (N64 >= 0 ? N64 : n64); ++it) {
 #pragma unroll
     for (int i = 0; i < W; ++i) {
       const double es = e * s[i];
       const double ec = e * c[i];
-      const double f = (E[i] - m[i]) - es;
+      const double f = (E[i] - m[i]) - es;     // NaN m (NaN / inf anomaly) poisons d -> rejected
       const double a = 1.0 - ec;
       const double a2 = a * a;
       const double t = ffma(-0.5 * f, es, a2);
       const double u = ffma(-f, es, a2);
-      const double v = (f * f) * (ec * (1.0 / 6.0));
+      const double v = (f * f) * (ec * RVK(19));
       const double den = ffma(a, u, v);
       const double d = -(f * t) * rcp64(den);
       // rotate (s, c) by d:  sin d = d - d^3/6,  cos d - 1 = -d^2/2 + d^4/24
       const double d2 = d * d;
-      const double sd = ffma(d * d2, -1.0 / 6.0, d);
-      const double cd1 = d2 * ffma(d2, 1.0 / 24.0, -0.5);
+      const double sd = ffma(d * d2, RVK(21), d);
+      const double cd1 = d2 * ffma(d2, RVK(20), -0.5);
       const double sn = ffma(s[i], cd1, ffma(c[i], sd, s[i]));
       const double cn = ffma(c[i], cd1, ffma(-s[i], sd, c[i]));
       s[i] = sn;
       c[i] = cn;
       E[i] += d;
-      dlast[i] = fabs(d);
+      dlast[i] = d;
     }
   }
 #pragma unroll
   for (int i = 0; i < W; ++i) {
     cosE[i] = c[i];
-    sinE[i] = neg[i] ? -s[i] : s[i];
+    sinE[i] = xor_hi(s[i], sign[i]);
   }
 }
 
 // Robust scalar fallback: f is increasing and convex on [0, pi], so Newton started from the
 // right of the root (f >= 0) descends monotonically onto it; bisection bounds guard the
-// round-off end game.  Full-precision libm sin/cos, convergence-tested, capped.
+// round-off end game.  Convergence-tested, capped.
 struct CosSin { double c, s; };
 
 RV_SLOW CosSin kepler_robust(double M, double e) {
   CosSin out;
   double m;
-  bool neg;
-  reduce_anomaly(M, m, neg);
+  int sign;
+  if (anomaly_is_big(M)) split_sign(reduce_big(M), m, sign);
+  else reduce_anomaly(M, m, sign);
   if (!(m == m)) { out.c = m; out.s = m; return out; }
   double lo = m, hi = m + e;
   if (hi > PI_D) hi = PI_D;
@@ -283,7 +354,7 @@ RV_SLOW CosSin kepler_robust(double M, double e) {
   double s, c;
   sincos_0pi(E, (float)E, s, c);
   out.c = c;
-  out.s = neg ? -s : s;
+  out.s = xor_hi(s, sign);
   return out;
 }
 
@@ -370,48 +441,73 @@ RV_HD double mean_anomaly(double n, double t, double tp) {
 #endif
 }
 
+RV_SLOW double cos_big(double x) { return cos(x); }
+
 RV_HD double cos_full(double x) {
   // cos of an unreduced angle via the same reduction + kernels (circular branch, model.py:242)
   double m;
-  bool neg;
-  reduce_anomaly(x, m, neg);
+  int sign;
+  reduce_anomaly(x, m, sign);
   double s, c;
   sincos_0pi(m, (float)m, s, c);
   return c;
 }
 
+// Adds one planet's RV at W epochs into rv[] (model.py:216-243 + 327; fit.py:3630's `+=`).
+// The constant K e cos w term is NOT added here: the caller folds the planets' C terms into one
+// per-sample constant.
 template <int W>
-RV_HD void planet_rv(const PlanetConst& pc, const SolverPlan& plan, const double (&t)[W],
-                     double (&rv)[W]) {
+RV_HD void planet_rv_add(const PlanetConst& pc, const SolverPlan& plan, const double (&t)[W],
+                         double (&rv)[W]) {
   double M[W];
 #pragma unroll
   for (int i = 0; i < W; ++i) M[i] = mean_anomaly(pc.n, t[i], pc.tp);
-  if (pc.e == 0) {                          // model.py:239-242
+  if (pc.e == 0) {                          // model.py:239-242, e * cos(w) == 0 exactly
+    bool big = false;
+    double x[W], cx[W];
 #pragma unroll
     for (int i = 0; i < W; ++i) {
 #if defined(__CUDA_ARCH__)
-      const double x = __dadd_rn(M[i], pc.w);
+      x[i] = __dadd_rn(M[i], pc.w);
 #else
       volatile double x0 = M[i] + pc.w;
-      const double x = x0;
+      x[i] = x0;
 #endif
-      rv[i] = pc.K * cos_full(x);            // e * cos(w) == 0 exactly
+      big |= anomaly_is_big(x[i]);
+      cx[i] = cos_full(x[i]);
     }
+    if (RV_ANY(big)) {
+#pragma unroll
+      for (int i = 0; i < W; ++i)
+        if (anomaly_is_big(x[i])) cx[i] = cos_big(x[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < W; ++i) rv[i] = ffma(pc.K, cx[i], rv[i]);
     return;
   }
   double cE[W], sE[W], dl[W];
-  kepler_fast<W>(M, pc.e, plan.n32, plan.n64, cE, sE, dl);
+  if (plan.n64 == 1 && plan.n32 == 1) kepler_fast<W, 1, 1>(M, pc.e, 1, 1, cE, sE, dl);
+  else if (plan.n64 == 1 && plan.n32 == 2) kepler_fast<W, 2, 1>(M, pc.e, 2, 1, cE, sE, dl);
+  else kepler_fast<W>(M, pc.e, plan.n32, plan.n64, cE, sE, dl);
+  bool bad = false;
+#pragma unroll
+  for (int i = 0; i < W; ++i) bad |= step_rejected(dl[i], plan.tol) || anomaly_is_big(M[i]);
+  if (RV_ANY(bad)) {                        // warp-uniform branch; rare
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      if (step_rejected(dl[i], plan.tol) || anomaly_is_big(M[i])) {
+        const CosSin cs = kepler_robust(M[i], pc.e);
+        cE[i] = cs.c;
+        sE[i] = cs.s;
+      }
+    }
+  }
 #pragma unroll
   for (int i = 0; i < W; ++i) {
-    if (!(dl[i] <= plan.tol) && (M[i] == M[i])) {
-      const CosSin cs = kepler_robust(M[i], pc.e);
-      cE[i] = cs.c;
-      sE[i] = cs.s;
-    }
-    // model.py:119-121, 170 with K, cos w, sin w folded into A, B, C
+    // model.py:119-121, 170 with K, cos w, sin w folded into A, B, C (C == e A)
     const double r = rcp64(ffma(-pc.e, cE[i], 1.0));
-    const double u = ffma(-sE[i], pc.B, ffma(cE[i], pc.A, -pc.e * pc.A));
-    rv[i] = ffma(r, u, pc.C);
+    const double u = ffma(-sE[i], pc.B, ffma(cE[i], pc.A, -pc.C));
+    rv[i] = ffma(r, u, rv[i]);
   }
 }
 

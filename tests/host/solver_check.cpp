@@ -49,9 +49,7 @@ int main(int argc, char** argv) {
       kepler_fast<2>(M, e, plan.n32, plan.n64, cE, sE, dl);
       for (int q = 0; q < 2; ++q) {
         ++ntot;
-        if (!(dl[q] <= plan.tol)) { ++nfb; CosSin cs = kepler_robust(M[q], e); cE[q] = cs.c; sE[q] = cs.s; }
-        double m; bool neg;
-        reduce_anomaly(M[q], m, neg);
+        if (step_rejected(dl[q], plan.tol) || anomaly_is_big(M[q])) { ++nfb; CosSin cs = kepler_robust(M[q], e); cE[q] = cs.c; sE[q] = cs.s; }
         // exact reduction in long double for the truth
         long double Ml = (long double)M[q];
         long double k = rintl(Ml / (2 * M_PIl));
