@@ -69,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(self.device)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "20", "-i", str(self.device)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -177,7 +177,7 @@ def time_kernel(torch, fn, steps: int, warmup: int, barrier) -> float:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=list(WORKLOADS))
@@ -268,14 +268,22 @@ def main() -> None:
         roofline = None
         if fpu:
             achieved = per_gpu_units_per_s * fpu / 1e12
+            traffic = None
+            try:      # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this launch shape
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(name)
+                if tj and tj["samples"] == S:
+                    traffic = tj["dram_bytes_per_launch"]
+            except Exception:
+                traffic = None
             roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_flops / 1e12, "unit": "TFLOP/s",
-                        "frac": achieved / (peak_flops / 1e12), "traffic": None,
+                        "frac": achieved / (peak_flops / 1e12), "traffic": traffic,
                         "peak_source": "measured live: dependent-free DFMA kernel (rvlp_measure_fp64_peak), burst",
                         "flops_per_unit": fpu, "kernel": "rvlp::logprob_kernel",
                         "kernel_ms_per_launch": ms_kernel / args.steps,
                         "algorithmic_hbm_bytes_per_launch": S * (theta.shape[1] + 1) * 8,
-                        "note": "frac > 1 is possible: the kernel needs ~3.5x fewer fp64 operations per unit than the "
-                                "reference algorithm the 418-FLOP figure counts (fp32 starter + one 4th-order step)"}
+                        "note": "frac > 1 is expected: the 418-FLOP/unit figure counts the REFERENCE algorithm (4 Halley "
+                                "passes with a libm sincos each); this kernel needs ~56 fp64 instructions per unit (fp32 "
+                                "starter + one fp64 step). Hardware view: profiles/ (ncu sm__inst_executed_pipe_fp64)"}
         line = {
             "metric": "kepler_rv_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,

@@ -129,7 +129,7 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
   DevProblem& P = c->P;
   P.n_planets = d->n_planets; P.par = d->parameterisation; P.n_inst = d->n_inst; P.ndim = d->ndim;
   P.n_priors = d->n_priors; P.n_hyper = d->n_hyper; P.n_model = n_model; P.n_epochs = (int)n_epochs;
-  P.n_pad = (int)((n_epochs + 32 * kW - 1) / (32 * kW) * (32 * kW));   // multiple of 64: bulk copy needs 16 B
+  P.n_pad = (int)((n_epochs + kPadTo - 1) / kPadTo * kPadTo);   // whole lane groups; x28 B is a multiple of 16 for the bulk copy
   P.t0 = d->t0; P.jacobian = d->jacobian; P.renorm = d->renorm;
 
   // packed, padded epoch block: [t | vel | velerr^2] doubles + int32 instrument ids

@@ -24,9 +24,27 @@ namespace rvlp {
 #ifndef RVLP_MIN_BLOCKS
 #define RVLP_MIN_BLOCKS 2
 #endif
-constexpr int kThreads = 256;
+#ifndef RVLP_THREADS
+#define RVLP_THREADS 256
+#endif
+constexpr int kThreads = RVLP_THREADS;
 constexpr int kWarps = kThreads / 32;
-constexpr int kW = RVLP_W;        // epochs per lane in flight (ILP)
+#ifndef RVLP_WP
+#define RVLP_WP 2
+#endif
+// Bit mask: software-pipelined sample evaluation (see sample_chi_pipelined) for samples whose planets all
+// take the lite plan (bit 0) / all have e <= 0.97 (bit 1).  Measured on B200 (profiles/r01_sweep5/6.log):
+// pipelining helps the mixed-plan high-e workload (+8% on config 4) and costs 9% on the all-lite config 3.
+#ifndef RVLP_PIPELINE
+#define RVLP_PIPELINE 2
+#endif
+#ifndef RVLP_STAGGER_NS        // experiment: delay every other warp pair at kernel start
+#define RVLP_STAGGER_NS 0
+#endif
+constexpr int kW = RVLP_W;        // epochs per lane in flight (ILP) in the generic path
+constexpr int kWP = RVLP_WP;      // same, in the software-pipelined paths
+constexpr int cgcd(int a, int b) { return b == 0 ? a : cgcd(b, a % b); }
+constexpr int kPadTo = 32 * (kW / cgcd(kW, kWP) * kWP);   // n_pad granularity: whole lane groups for both paths
 constexpr int kG = 4;             // samples whose prologue a warp does together
 constexpr int kPlanetRec = 16;    // doubles per planet in the sample record
 constexpr double kLog2Pi = 1.8378770664093453;   // np.log(2*np.pi), fit.py:3595
@@ -47,7 +65,9 @@ __host__ __device__ inline int sample_rec_doubles(int n_planets, int n_inst) {
 }
 // sample record: [0] lp  [1] flags  [2] gd  [3] gdd  [4] lhp  [5] sum_k C_k  [6..) gamma[n_inst]  jit2[n_inst]  planets
 // planet record: n tp e A B C w K | tol plan(bits) P Kraw e w tp invalid
-enum { F_JIT = 1, F_PLANET = 2, F_PRIOR = 4, F_HYPER = 8, F_SKIP = 16 };
+enum { F_JIT = 1, F_PLANET = 2, F_PRIOR = 4, F_HYPER = 8, F_SKIP = 16,
+       F_CLS_LITE = 32,   // every planet 0 < e <= 0.65: pipelined (1 fp32 step, lite fp64 step)
+       F_CLS_FULL = 64 }; // every planet 0 < e <= 0.97: pipelined (2 fp32 steps, 4th-order fp64 step)
 
 struct SmemLayout {
   int off_t, off_v, off_e2, off_inst, off_priors, off_srccol, off_srcconst, off_scratch, total;
@@ -202,11 +222,17 @@ __device__ __forceinline__ void sample_prologue(const DevProblem& P, const Table
     }
     const double* planets = sr + kHdr + 2 * P.n_inst;
     double csum = 0.0;
+    bool all_lite = npl > 0, all_full = npl > 0;
     for (int k = 0; k < npl; ++k) {
       if (planets[k * kPlanetRec + 15] != 0.0) flags |= F_PLANET;
       csum += planets[k * kPlanetRec + 5];                  // K e cos w of every planet (model.py:170)
+      const double e = planets[k * kPlanetRec + 2];
+      all_lite = all_lite && (e > 0.0) && (e <= 0.65);
+      all_full = all_full && (e > 0.0) && (e <= 0.97);
     }
     sr[5] = csum;
+    if (all_lite) flags |= F_CLS_LITE;
+    else if (all_full) flags |= F_CLS_FULL;
     if (P.n_hyper) {                                        // gp.py:98-108
       for (int k = 0; k < 4; ++k) {
         const double h = model_param(T, row, P.n_model + k);
@@ -265,6 +291,150 @@ __device__ __forceinline__ void model_rv(const DevProblem& P, const double* sr, 
   }
 }
 
+// Lane-local accumulators of one sample's chi^2 + log-det sum (fixed epoch order per lane).
+// sum_i ln var_i is kept as a running product of the variances' mantissas plus an integer exponent sum:
+// one log per lane per sample instead of one per epoch.
+struct ChiAcc {
+  double chi = 0.0, prodm = 1.0, slow = 0.0;
+  int exsum = 0, cnt = 0;
+};
+
+// Consumes the model RV (planets + trend) at epochs base + j*32 + lane (fit.py:3642-3658).
+template <int W>
+__device__ __forceinline__ void chi_epilogue(const DevProblem& P, const Tables& T, const double* sr, int base,
+                                             int lane, const double (&rv)[W], ChiAcc& a) {
+  double var[W], res[W];
+  bool odd = false;
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    const int idx = base + j * 32 + lane;
+    const int in = T.inst[idx];
+    const double tot = rv[j] + sr[kHdr + in];             // fit.py:3642-3644
+    var[j] = T.e2[idx] + sr[kHdr + P.n_inst + in];        // fit.py:3654
+    res[j] = tot - T.v[idx];
+    const int h = __double2hiint(var[j]);
+    const bool normal = (unsigned)(h - 0x00100000) < 0x7fe00000u;   // positive, normal, finite
+    const bool live = idx < P.n_epochs;
+    odd |= live && !normal;
+    if (live && normal) {                                 // fit.py:3655-3658
+      a.chi = fma(res[j] * res[j], rcp64(var[j]), a.chi);
+      a.prodm *= __hiloint2double((h & 0x000fffff) | 0x3ff00000, __double2loint(var[j]));
+      a.exsum += (h >> 20) - 1023;
+      a.cnt += 1;
+    }
+  }
+  if (__any_sync(0xffffffffu, odd)) {                     // var == 0, denormal, inf, NaN: IEEE path
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const int idx = base + j * 32 + lane;
+      const int h = __double2hiint(var[j]);
+      if (idx < P.n_epochs && !((unsigned)(h - 0x00100000) < 0x7fe00000u))
+        a.slow += res[j] * res[j] / var[j] + (kLog2Pi + log(var[j]));
+    }
+  }
+}
+
+__device__ __forceinline__ double chi_finish(const ChiAcc& a) {
+  double acc = a.chi + ((double)a.cnt * kLog2Pi + fma((double)a.exsum, 0.6931471805599453, log(a.prodm))) + a.slow;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
+struct HotPlanet { double n, tp, e, A, B, C, tol; };
+__device__ __forceinline__ HotPlanet load_hot(const double2* planets, int k) {
+  const double2* pr = planets + k * (kPlanetRec / 2);
+  const double2 a = pr[0], b = pr[1], c = pr[2], e = pr[4];
+  HotPlanet h;
+  h.n = a.x; h.tp = a.y; h.e = b.x; h.A = b.y; h.B = c.x; h.C = c.y; h.tol = e.x;
+  return h;
+}
+
+// Software-pipelined evaluation of one sample whose planets all share a compile-time solver plan.
+// The (epoch group, planet) double loop is flattened; in every iteration stage A (fp32 / MUFU pipes) of the
+// NEXT (group, planet) is issued next to stage B (fp64 pipe) of the current one.  They are independent, so
+// each warp's instruction stream mixes the two pipes instead of alternating long single-pipe phases (which
+// leaves the 2-cycle-issue FP64 pipe's gaps unfilled when all warps of an SM run in lock-step).
+template <int W, int N32, int N64>
+__device__ __forceinline__ void sample_chi_pipelined(const DevProblem& P, const Tables& T, const double* sr, int lane,
+                                                     double tol, ChiAcc& acc) {
+  const int npl = P.n_planets;
+  const int G = P.n_pad / (32 * W);
+  const double2* planets = reinterpret_cast<const double2*>(sr + kHdr + 2 * P.n_inst);
+  const double c0 = sr[5], gd = sr[2], gdd = sr[3];
+  double tt[W], M[W], rv[W];
+#pragma unroll
+  for (int j = 0; j < W; ++j) tt[j] = T.t[j * 32 + lane];
+  HotPlanet pc = load_hot(planets, 0);
+  bool bigA = false;
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    M[j] = mean_anomaly(pc.n, tt[j], pc.tp);
+    bigA |= anomaly_is_big(M[j]);
+    rv[j] = c0;
+  }
+  StarterOut<W> A;
+  kepler_stage_a<W, N32>(M, pc.e, N32, A);
+  int k = 0, g = 0;
+  const int Q = G * npl;
+  for (int q = 0; q < Q; ++q) {
+    int kn = k + 1, gn = g;
+    if (kn == npl) { kn = 0; gn = g + 1; }
+    const int gl = gn < G ? gn : G - 1;                    // the last iteration's look-ahead is discarded
+    double tn[W], Mn[W];
+    const HotPlanet pn = load_hot(planets, kn);
+    bool bigN = false;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      tn[j] = T.t[gl * 32 * W + j * 32 + lane];
+      Mn[j] = mean_anomaly(pn.n, tn[j], pn.tp);
+      bigN |= anomaly_is_big(Mn[j]);
+    }
+    StarterOut<W> An;
+    kepler_stage_a<W, N32>(Mn, pn.e, N32, An);             // next: fp32 / MUFU
+
+    double cE[W], sE[W], dl[W], ri[W];
+    kepler_stage_b<W, N64>(A, pc.e, N64, cE, sE, dl, ri);  // current: fp64
+    bool bad = bigA;
+#pragma unroll
+    for (int j = 0; j < W; ++j) bad |= step_rejected(dl[j], tol);
+    if (__any_sync(0xffffffffu, bad)) {                    // warp-uniform, rare
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        const double Mj = mean_anomaly(pc.n, tt[j], pc.tp);
+        if (step_rejected(dl[j], tol) || anomaly_is_big(Mj)) {
+          const CosSin cs = kepler_robust(Mj, pc.e);
+          cE[j] = cs.c;
+          sE[j] = cs.s;
+          ri[j] = 1.0 / (1.0 - pc.e * cs.c);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      const double u = fma(-sE[j], pc.B, fma(cE[j], pc.A, -pc.C));
+      rv[j] = fma(ri[j], u, rv[j]);
+    }
+    if (k == npl - 1) {                                    // all planets of this epoch group done
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        const double dt = tt[j] - P.t0;                    // model.py:483-509
+        rv[j] = fma(gdd, dt * dt, fma(gd, dt, rv[j]));
+      }
+      chi_epilogue<W>(P, T, sr, g * 32 * W, lane, rv, acc);
+#pragma unroll
+      for (int j = 0; j < W; ++j) rv[j] = c0;
+    }
+    A = An;
+    pc = pn;
+    bigA = bigN;
+#pragma unroll
+    for (int j = 0; j < W; ++j) tt[j] = tn[j];
+    k = kn;
+    g = gn;
+  }
+}
+
 // ------------------------------------------------------------------ K1: log-probability
 __global__ void __launch_bounds__(kThreads, RVLP_MIN_BLOCKS)
 logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double* __restrict__ out,
@@ -278,6 +448,9 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
   double* scratch = reinterpret_cast<double*>(smem + L.off_scratch) + warp * kG * rec;
   const int64_t n_batches = (S + kG - 1) / kG;
   const int64_t gw = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
+#if RVLP_STAGGER_NS > 0
+  if ((warp >> 2) & 1) __nanosleep(RVLP_STAGGER_NS);
+#endif
 
   for (int64_t b = gw; b < n_batches; b += nw) {
     const int64_t s0 = b * kG;
@@ -294,52 +467,21 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
       } else if ((flags & (F_JIT | F_PRIOR)) && ll_out == nullptr) {
         ll = 0.0;                                            // result is -inf regardless: skip the work
       } else {
-        // Lane partials in fixed epoch order: chi^2 sum, product of the variances' mantissas and
-        // sum of their exponents (sum_i ln var_i = ln prod mant_i + ln2 sum ex_i: one log per lane
-        // per sample instead of one per epoch).
-        double chi = 0.0, prodm = 1.0, slow = 0.0;
-        int exsum = 0, cnt = 0;
-        for (int base = 0; base < P.n_pad; base += 32 * kW) {
-          double tt[kW], rv[kW];
-          int idx[kW];
+        ChiAcc acc;
+        if ((RVLP_PIPELINE & 1) && (flags & F_CLS_LITE)) {
+          sample_chi_pipelined<kWP, 1, 0>(P, T, sr, lane, 4.0e-6, acc);
+        } else if ((RVLP_PIPELINE & 2) && (flags & F_CLS_FULL)) {
+          sample_chi_pipelined<kWP, 2, 1>(P, T, sr, lane, 2.5e-4, acc);
+        } else {
+          for (int base = 0; base < P.n_pad; base += 32 * kW) {
+            double tt[kW], rv[kW];
 #pragma unroll
-          for (int j = 0; j < kW; ++j) {
-            idx[j] = base + j * 32 + lane;
-            tt[j] = T.t[idx[j]];
-          }
-          model_rv<kW>(P, sr, tt, rv, -1, true);
-          double var[kW], res[kW];
-          bool odd = false;
-#pragma unroll
-          for (int j = 0; j < kW; ++j) {
-            const int in = T.inst[idx[j]];
-            const double tot = rv[j] + sr[kHdr + in];           // fit.py:3642-3644
-            var[j] = T.e2[idx[j]] + sr[kHdr + P.n_inst + in];   // fit.py:3654
-            res[j] = tot - T.v[idx[j]];
-            const int h = __double2hiint(var[j]);
-            const bool normal = (unsigned)(h - 0x00100000) < 0x7fe00000u;   // positive, normal, finite
-            const bool live = idx[j] < P.n_epochs;
-            odd |= live && !normal;
-            if (live && normal) {                               // fit.py:3655-3658
-              chi = fma(res[j] * res[j], rcp64(var[j]), chi);
-              prodm *= __hiloint2double((h & 0x000fffff) | 0x3ff00000, __double2loint(var[j]));
-              exsum += (h >> 20) - 1023;
-              cnt += 1;
-            }
-          }
-          if (__any_sync(0xffffffffu, odd)) {                   // var == 0, denormal, inf, NaN: IEEE path
-#pragma unroll
-            for (int j = 0; j < kW; ++j) {
-              const int h = __double2hiint(var[j]);
-              if (idx[j] < P.n_epochs && !((unsigned)(h - 0x00100000) < 0x7fe00000u))
-                slow += res[j] * res[j] / var[j] + (kLog2Pi + log(var[j]));
-            }
+            for (int j = 0; j < kW; ++j) tt[j] = T.t[base + j * 32 + lane];
+            model_rv<kW>(P, sr, tt, rv, -1, true);
+            chi_epilogue<kW>(P, T, sr, base, lane, rv, acc);
           }
         }
-        double acc = chi + ((double)cnt * kLog2Pi + fma((double)exsum, 0.6931471805599453, log(prodm))) + slow;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        ll = -0.5 * acc;
+        ll = -0.5 * chi_finish(acc);
       }
       if (lane == 0) {
         double r;
@@ -473,15 +615,18 @@ __global__ void prior_kernel(rvlp_prior pr, const double* __restrict__ x, int64_
     out[i] = prior_logpdf(pr, x[i]);
 }
 
-// Dependent-free DFMA loop: 8 independent chains per thread, 2 flops per DFMA.
+// Dependent-free DFMA loop: 8 independent chains per thread, 2 flops per DFMA, in the fastest operand form
+// measured on B200 (tools/pipe_probe2.cu: DFMA R,R,R,c issues every 2.08 cycles per SMSP; with three register
+// operands it drops to one per 3.06 cycles - register-file bandwidth).
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
          x7 = x0 + 7;
+  const double y = a + 1e-12 * threadIdx.x;   // a per-thread register multiplier
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+      x0 = fma(x0, y, b); x1 = fma(x1, y, b); x2 = fma(x2, y, b); x3 = fma(x3, y, b);
+      x4 = fma(x4, y, b); x5 = fma(x5, y, b); x6 = fma(x6, y, b); x7 = fma(x7, y, b);
     }
   }
   out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));

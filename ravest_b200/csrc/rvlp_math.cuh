@@ -143,6 +143,15 @@ RV_HD void sincos_0pi_f32(float E, float& s, float& c) {
 #else
   s = sinf(E);
   c = cosf(E);
+#if defined(RVLP_EMULATE_MUFU)
+  // host-only stress knob for tests/host/solver_check.cpp: worst-case MUFU.SIN/COS error (2^-20.9 abs)
+  // with a pseudo-random sign, plus the fp32 range-reduction multiply's rounding
+  uint32_t b;
+  memcpy(&b, &E, 4);
+  b = b * 2654435761u;
+  s += (b & 0x10000u) ? 5.2e-7f : -5.2e-7f;
+  c += (b & 0x20000u) ? 5.2e-7f : -5.2e-7f;
+#endif
 #endif
 }
 
@@ -219,7 +228,7 @@ RV_HD void reduce_anomaly(double M, double& m, int& sign) {
 //     contract enough, or whose |M| is huge, through kepler_robust.
 struct SolverPlan {
   int n32;       // fp32 Halley iterations
-  int n64;       // fp64 Householder steps
+  int n64;       // fp64 steps; 0 selects the "lite" plan (one Halley step, see kepler_fast)
   double tol;    // acceptance bound on the last fp64 step
 };
 
@@ -229,12 +238,15 @@ RV_HD SolverPlan plan_for(double e) {
   //   (1,1): 4.5e-5 at e = 0.80 (2.1e-4 at 0.85, inaccurate from 0.9)
   //   (2,1): 1.2e-5 at e = 0.97 (8.4e-5 at 0.98, inaccurate from 0.99)
   //   (2,2) holds to 0.99, (3,3) to 0.999.
-  if (e <= 0.80) { p.n32 = 1; p.n64 = 1; }
+  //   lite (one fp32 + one fp64 *Halley* step): the fp32 stage leaves <= 5.4e-7 at e = 0.6 and
+  //   2.4e-6 at e = 0.7, so a third-order step is already at round-off for e <= 0.65.
+  if (e <= 0.65) { p.n32 = 1; p.n64 = 0; }
+  else if (e <= 0.80) { p.n32 = 1; p.n64 = 1; }
   else if (e <= 0.97) { p.n32 = 2; p.n64 = 1; }
   else if (e <= 0.99) { p.n32 = 2; p.n64 = 2; }
   else { p.n32 = 3; p.n64 = 3; }
   // a last step of size d leaves an error ~ K4 d^4; 2.5e-4 measured safe for every plan
-  p.tol = (e <= 0.97) ? 2.5e-4 : 1.0e-5;
+  p.tol = (e <= 0.65) ? 4.0e-6 : ((e <= 0.97) ? 2.5e-4 : 1.0e-5);
   if (!(e <= 0.999)) p.tol = -1.0;   // always take the robust path (also e = NaN)
   return p;
 }
@@ -244,51 +256,92 @@ RV_HD bool step_rejected(double dlast, double tol) {
   return (hi32(dlast) & 0x7fffffff) >= hi32(tol) || hi32(tol) < 0;
 }
 
-// N32 / N64 >= 0 fix the iteration counts at compile time (straight-line code for the two plans
-// that cover e <= 0.97); -1 reads them from n32 / n64.
-template <int W, int N32 = -1, int N64 = -1>
-RV_HD void kepler_fast(const double (&M)[W], double e, int n32, int n64, double (&cosE)[W],
-                       double (&sinE)[W], double (&dlast)[W]) {
-  if (N32 >= 0) n32 = N32;
-  if (N64 >= 0) n64 = N64;
+// The solver in two stages so that callers can software-pipeline them (stage A of the next
+// planet is independent of stage B of the current one, and uses different pipes).
+//
+// Stage A (fp32 / MUFU pipes + 5 fp64 ops): reduce M, starter, N32 fp32 Halley steps.
+template <int W>
+struct StarterOut {
+  double m[W];     // reduced anomaly in [0, pi]
+  float Ef[W];     // fp32 estimate of E, clamped to [0, pi]
+  int sign[W];     // sign bit of the reduced anomaly (E(-M) = -E(M))
+};
+
+template <int W, int N32 = -1>
+RV_HD void kepler_stage_a(const double (&M)[W], double e, int n32, StarterOut<W>& o) {
   const float ef = (float)e;
   const float one_p_e2 = ffmaf(ef, ef, 1.0f);
   const float m2e = -2.0f * ef;
-  double m[W];
-  int sign[W];
-  float Ef[W], mf[W];
+  float mf[W];
 #pragma unroll
   for (int i = 0; i < W; ++i) {
-    reduce_anomaly(M[i], m[i], sign[i]);
-    mf[i] = (float)m[i];
+    reduce_anomaly(M[i], o.m[i], o.sign[i]);
+    mf[i] = (float)o.m[i];
     float s, c;
     sincos_0pi_f32(mf[i], s, c);
     // q = |1 - e exp(i m)|^2 >= (1 - e)^2 > 0; a rounding-negative q gives NaN, which the clamp at the
     // end of the fp32 stage turns into E0 = 0 and the step test then rejects
     const float q = ffmaf(m2e, c, one_p_e2);
-    Ef[i] = ffmaf(ef * s, rsqrt32(q), mf[i]);
+    o.Ef[i] = ffmaf(ef * s, rsqrt32(q), mf[i]);
   }
 #pragma unroll
   for (int it = 0; it < (N32 >= 0 ? N32 : n32); ++it) {
 #pragma unroll
     for (int i = 0; i < W; ++i) {
       float s, c;
-      sincos_0pi_f32(Ef[i], s, c);
+      sincos_0pi_f32(o.Ef[i], s, c);
       const float es = ef * s;
-      const float f = (Ef[i] - mf[i]) - es;
+      const float f = (o.Ef[i] - mf[i]) - es;
       const float fp = ffmaf(-ef, c, 1.0f);
       const float den = ffmaf(fp, fp, -0.5f * f * es);
       const float d = f * fp * rcp32(den);
-      Ef[i] = Ef[i] - d;
+      o.Ef[i] = o.Ef[i] - d;
     }
   }
+#pragma unroll
+  for (int i = 0; i < W; ++i)   // the fp64 kernels need E0 in [0, pi]; NaN -> 0
+    o.Ef[i] = fminf(fmaxf(o.Ef[i], 0.0f), 3.14159274f);
+}
+
+// Stage B (fp64 pipe): one sincos of E0, then the fp64 step(s).
+// N64 >= 0 fixes the step count at compile time (straight-line code for the plans that cover
+// e <= 0.97); -1 reads it from n64.
+// N64 == 0 is the "lite" plan for e <= 0.65: the fp32 stage already lands within ~1e-6, so ONE
+// third-order (Halley) step written as a series in f/f' suffices, the rotation needs only second
+// order, and 1/(1 - e cos E) follows from 1/f'(E0) by a two-term Newton update (no second MUFU seed).
+// rinv = 1 / (1 - e cos E), the factor model.py:119-121 divides by.
+template <int W, int N64 = -1>
+RV_HD void kepler_stage_b(const StarterOut<W>& o, double e, int n64, double (&cosE)[W], double (&sinE)[W],
+                          double (&dlast)[W], double (&rinv)[W]) {
+  const double (&m)[W] = o.m;
+  const int (&sign)[W] = o.sign;
   double E[W], s[W], c[W];
 #pragma unroll
   for (int i = 0; i < W; ++i) {
-    Ef[i] = fminf(fmaxf(Ef[i], 0.0f), 3.14159274f);   // the fp64 kernels need E0 in [0, pi]; NaN -> 0
-    E[i] = (double)Ef[i];
-    sincos_0pi(E[i], Ef[i], s[i], c[i]);
+    E[i] = (double)o.Ef[i];
+    sincos_0pi(E[i], o.Ef[i], s[i], c[i]);
     dlast[i] = 0.0;
+  }
+  if (N64 == 0) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      const double es = e * s[i];
+      const double f = (E[i] - m[i]) - es;     // NaN m (NaN / inf anomaly) poisons d -> rejected
+      const double a = ffma(-e, c[i], 1.0);
+      const double ra = rcp64(a);
+      const double x = f * ra;                 // Newton step, |x| <~ 1e-6
+      const double y = es * ra;
+      const double d = -x * ffma(0.5 * x, y, 1.0);     // Halley: -x / (1 - x y / 2), next term ~1e-19
+      const double h = -0.5 * (d * d);
+      const double sn = ffma(s[i], h, ffma(c[i], d, s[i]));
+      const double cn = ffma(c[i], h, ffma(-s[i], d, c[i]));
+      const double eps = ffma(ffma(e, cn, -1.0), ra, 1.0);   // 1 - (1 - e cos E) / a
+      rinv[i] = ffma(ra, ffma(eps, eps, eps), ra);
+      cosE[i] = cn;
+      sinE[i] = xor_hi(sn, sign[i]);
+      dlast[i] = d;
+    }
+    return;
   }
 #pragma unroll
   for (int it = 0; it < (N64 >= 0 ? N64 : n64); ++it) {
@@ -306,21 +359,39 @@ RV_HD void kepler_fast(const double (&M)[W], double e, int n32, int n64, double 
       const double d = -(f * t) * rcp64(den);
       // rotate (s, c) by d:  sin d = d - d^3/6,  cos d - 1 = -d^2/2 + d^4/24
       const double d2 = d * d;
-      const double sd = ffma(d * d2, RVK(21), d);
-      const double cd1 = d2 * ffma(d2, RVK(20), -0.5);
+      double sd, cd1;
+      if (N64 >= 0) {   // single-step plans: |d| <= 2.5e-4, series error < 1e-20
+        sd = ffma(d * d2, RVK(21), d);
+        cd1 = d2 * ffma(d2, RVK(20), -0.5);
+      } else {          // multi-step plans (e > 0.97): early steps reach 3e-3 and 1/(1-e) amplifies any drift
+        sd = ffma(d * d2, ffma(d2, 1.0 / 120.0, RVK(21)), d);
+        cd1 = d2 * ffma(d2, ffma(d2, -1.0 / 720.0, RVK(20)), -0.5);
+      }
       const double sn = ffma(s[i], cd1, ffma(c[i], sd, s[i]));
       const double cn = ffma(c[i], cd1, ffma(-s[i], sd, c[i]));
       s[i] = sn;
       c[i] = cn;
       E[i] += d;
-      dlast[i] = d;
+      // Multi-step plans: the rotation's series is only good to ~|d|^7/5040, and a later step cannot
+      // repair a drifted (s, c); an early step above 3e-3 therefore poisons the verdict (-> robust path).
+      if (it > 0 && (hi32(dlast[i]) & 0x7fffffff) >= 0x3f689374) dlast[i] = 1.0;
+      else dlast[i] = (it > 0 && dlast[i] == 1.0) ? 1.0 : d;
     }
   }
 #pragma unroll
   for (int i = 0; i < W; ++i) {
     cosE[i] = c[i];
     sinE[i] = xor_hi(s[i], sign[i]);
+    rinv[i] = rcp64(ffma(-e, c[i], 1.0));
   }
+}
+
+template <int W, int N32 = -1, int N64 = -1>
+RV_HD void kepler_fast(const double (&M)[W], double e, int n32, int n64, double (&cosE)[W],
+                       double (&sinE)[W], double (&dlast)[W], double (&rinv)[W]) {
+  StarterOut<W> o;
+  kepler_stage_a<W, N32>(M, e, n32, o);
+  kepler_stage_b<W, N64>(o, e, n64, cosE, sinE, dlast, rinv);
 }
 
 // Robust scalar fallback: f is increasing and convex on [0, pi], so Newton started from the
@@ -485,10 +556,11 @@ RV_HD void planet_rv_add(const PlanetConst& pc, const SolverPlan& plan, const do
     for (int i = 0; i < W; ++i) rv[i] = ffma(pc.K, cx[i], rv[i]);
     return;
   }
-  double cE[W], sE[W], dl[W];
-  if (plan.n64 == 1 && plan.n32 == 1) kepler_fast<W, 1, 1>(M, pc.e, 1, 1, cE, sE, dl);
-  else if (plan.n64 == 1 && plan.n32 == 2) kepler_fast<W, 2, 1>(M, pc.e, 2, 1, cE, sE, dl);
-  else kepler_fast<W>(M, pc.e, plan.n32, plan.n64, cE, sE, dl);
+  double cE[W], sE[W], dl[W], ri[W];
+  if (plan.n64 == 0) kepler_fast<W, 1, 0>(M, pc.e, 1, 0, cE, sE, dl, ri);
+  else if (plan.n64 == 1 && plan.n32 == 1) kepler_fast<W, 1, 1>(M, pc.e, 1, 1, cE, sE, dl, ri);
+  else if (plan.n64 == 1 && plan.n32 == 2) kepler_fast<W, 2, 1>(M, pc.e, 2, 1, cE, sE, dl, ri);
+  else kepler_fast<W>(M, pc.e, plan.n32, plan.n64, cE, sE, dl, ri);
   bool bad = false;
 #pragma unroll
   for (int i = 0; i < W; ++i) bad |= step_rejected(dl[i], plan.tol) || anomaly_is_big(M[i]);
@@ -499,15 +571,15 @@ RV_HD void planet_rv_add(const PlanetConst& pc, const SolverPlan& plan, const do
         const CosSin cs = kepler_robust(M[i], pc.e);
         cE[i] = cs.c;
         sE[i] = cs.s;
+        ri[i] = 1.0 / (1.0 - pc.e * cs.c);
       }
     }
   }
 #pragma unroll
   for (int i = 0; i < W; ++i) {
     // model.py:119-121, 170 with K, cos w, sin w folded into A, B, C (C == e A)
-    const double r = rcp64(ffma(-pc.e, cE[i], 1.0));
     const double u = ffma(-sE[i], pc.B, ffma(cE[i], pc.A, -pc.C));
-    rv[i] = ffma(r, u, rv[i]);
+    rv[i] = ffma(ri[i], u, rv[i]);
   }
 }
 

@@ -110,11 +110,15 @@ def test_prior_constructor_errors_match_reference():
     assert P.PRIOR_FUNCTIONS[3] == "TruncatedNormal"
 
 
-def test_host_compiled_solver_converges():
-    exe = "/tmp/rvlp_solver_check"
+@pytest.mark.parametrize("mufu", [False, True])
+def test_host_compiled_solver_converges(mufu):
+    """The solver (rvlp_math.cuh compiled for the host) over a dense (e, M) sweep against an 80-bit
+    reference; mufu=True injects the worst-case MUFU.SIN/COS error into the fp32 stage."""
+    exe = "/tmp/rvlp_solver_check" + ("_mufu" if mufu else "")
     src = os.path.join(ROOT, "tests", "host", "solver_check.cpp")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-mfma", "-o", exe, src, "-lm"], check=True)
-    res = subprocess.run([exe, "40000"], capture_output=True, text=True)
+    flags = ["-DRVLP_EMULATE_MUFU"] if mufu else []
+    subprocess.run(["g++", "-O2", "-std=c++17", "-mfma"] + flags + ["-o", exe, src, "-lm"], check=True)
+    res = subprocess.run([exe, "60000"], capture_output=True, text=True)
     assert res.returncode == 0, res.stdout
     lines = res.stdout.strip().splitlines()
     assert len(lines) >= 20
@@ -122,9 +126,9 @@ def test_host_compiled_solver_converges():
         fb = float(re.search(r"fallback=([0-9.]+)%", ln).group(1))
         e = float(re.search(r"e=(\S+)", ln).group(1))
         ratio = float(re.search(r"rv_err/cond=([0-9.]+)", ln).group(1))
-        assert ratio < 4.0, ln
-        if e <= 0.999:
-            assert fb == 0.0, ln
+        assert ratio < 4.0, ln            # error in units of the problem's own conditioning
+        if e <= 0.995:
+            assert fb == 0.0, ln          # the safety net is never needed where the fast plans apply
 
 
 def test_shard_bounds_cover_and_align():
