@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -77,7 +78,7 @@ struct rvlp_ctx {
   void* d_src_const = nullptr;
   void* d_priors = nullptr;
   void* d_epochs = nullptr;
-  int smem_main = 0, smem_gp = 0;
+  int smem_main = 0, smem_gp = 0, smem_gp_tiled = 0, gp_tile = 0;
   int max_smem = 0;
   // host-buffer path
   double* h_theta = nullptr;
@@ -188,6 +189,12 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
       return rc;
     }
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    c->gp_tile = gp_tile_for(P.n_epochs);
+    c->smem_gp_tiled = gp_tiled_smem(P, L).total;
+    CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   }
   CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 #undef CTX_TRY
@@ -310,9 +317,25 @@ int rvlp_gp_logprob_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
   if (S == 0) return RVLP_OK;
   DeviceGuard guard(c->device);
   int grid = 0;
-  int rc = grid_for(c->device, (const void*)gp_logprob_kernel, c->smem_gp, S, &grid);
-  if (rc) return rc;
-  gp_logprob_kernel<<<grid, kThreads, c->smem_gp, (cudaStream_t)stream>>>(c->P, theta_dev, S, out_dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+#define RVLP_GP_TILED(TT)                                                                                   \
+  case TT:                                                                                                  \
+    rc = grid_for(c->device, (const void*)gp_logprob_tiled_kernel<TT>, c->smem_gp_tiled, S, &grid);         \
+    if (rc) return rc;                                                                                      \
+    gp_logprob_tiled_kernel<TT><<<grid, kThreads, c->smem_gp_tiled, st>>>(c->P, theta_dev, S, out_dev);     \
+    break;
+  switch (getenv("RVLP_GP_SMEM_KERNEL") ? 0 : c->gp_tile) {
+    RVLP_GP_TILED(2)
+    RVLP_GP_TILED(4)
+    RVLP_GP_TILED(6)
+    RVLP_GP_TILED(8)
+    default:   // N > 175 epochs: shared-memory right-looking kernel
+      rc = grid_for(c->device, (const void*)gp_logprob_kernel, c->smem_gp, S, &grid);
+      if (rc) return rc;
+      gp_logprob_kernel<<<grid, kThreads, c->smem_gp, st>>>(c->P, theta_dev, S, out_dev);
+  }
+#undef RVLP_GP_TILED
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return RVLP_OK;

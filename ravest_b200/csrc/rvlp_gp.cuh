@@ -149,4 +149,198 @@ gp_logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, dou
   }
 }
 
+// ------------------------------------------------------------------ K3, register-tiled version
+// The whole lower triangle lives in REGISTERS: thread (I, J), I >= J, owns the T x T tile of rows
+// I*T.. and columns J*T..; row N is the residual (so the column sweeps forward-substitute it and
+// alpha = L^-1 r falls out).  Per column j: the owners of column j publish it to a double-buffered
+// shared-memory vector, ONE __syncthreads, then every thread scales by 1/sqrt(pivot) and applies the
+// rank-1 update to its tile with T + T shared loads per T*T FMAs.  N <= 22*T - 1 (T = 8: N <= 175).
+struct GpTiledSmem { int off_resid, off_col, total; };
+__host__ __device__ inline GpTiledSmem gp_tiled_smem(const DevProblem& P, const SmemLayout& L) {
+  GpTiledSmem G;
+  int o = (L.total + 15) & ~15;
+  const int rows = ((P.n_epochs + 1 + 16) + 1) & ~1;  // + padding rows of the last tile row; even: 16-byte rows
+  G.off_resid = o; o += rows * 8;
+  G.off_col = o; o += 2 * rows * 8;
+  G.total = o;
+  return G;
+}
+__host__ __device__ inline int gp_tile_for(int n_epochs) {
+  const int t[4] = {2, 4, 6, 8};
+  for (int i = 0; i < 4; ++i)
+    if (n_epochs + 1 <= 22 * t[i]) return t[i];
+  return 0;
+}
+
+template <int TT>
+__global__ void __launch_bounds__(kThreads, (TT >= 8 ? 1 : 2))
+gp_logprob_tiled_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout L = smem_layout(P);
+  const GpTiledSmem G = gp_tiled_smem(P, L);
+  stage_problem(P, L, smem);
+  const Tables T = tables_of(L, smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
+  double* scratch = reinterpret_cast<double*>(smem + L.off_scratch);
+  double* resid = reinterpret_cast<double*>(smem + G.off_resid);
+  double* colbuf = reinterpret_cast<double*>(smem + G.off_col);
+  const int N = P.n_epochs;
+  const int rows = ((N + 1 + 16) + 1) & ~1;
+  const int nt = (N + 1 + TT - 1) / TT;
+  // Tile coordinates of this thread: lower triangle enumerated COLUMN-major, so the lanes of a warp
+  // share (almost) one tile column J and therefore retire from the sweep together.
+  int J = 0, rem = tid;
+  while (J < nt && rem >= nt - J) { rem -= nt - J; ++J; }
+  const int I = J + rem;
+  const bool has_tile = J < nt;
+  const int r0 = I * TT, c0 = J * TT;
+
+  for (int64_t s = blockIdx.x; s < S; s += gridDim.x) {
+    if (warp == 0) sample_prologue(P, T, theta, s, s + 1, scratch, rec, lane, true);
+    __syncthreads();
+    const double* sr = scratch;
+    const int flags = __double2loint(sr[1]);
+    const double lp = sr[0], lhp = sr[4];
+    if (flags & (F_JIT | F_HYPER | F_PRIOR)) {               // fit.py:7857-7886
+      if (tid == 0) out[s] = -INFINITY;
+      __syncthreads();
+      continue;
+    }
+    int nonfinite = (flags & F_PLANET) ? 1 : 0;              // fit.py:8022-8024
+    if (!nonfinite) {
+      for (int i = tid; i < N; i += kThreads) {              // residual v - mean, fit.py:7994-8043, 8059
+        double tt[1] = {T.t[i]}, rv[1];
+        model_rv<1>(P, sr, tt, rv, -1, true);
+        const double mean = rv[0] + sr[kHdr + T.inst[i]];
+        if (!(fabs(mean) <= 1.79769313486231570e308)) nonfinite = 1;
+        resid[i] = T.v[i] - mean;
+      }
+    }
+    if (__syncthreads_or(nonfinite)) {                       // fit.py:8082-8083
+      if (tid == 0) {
+        double r = -INFINITY + lp + lhp;
+        r += P.jacobian;
+        r += P.renorm;
+        out[s] = r;
+      }
+      __syncthreads();
+      continue;
+    }
+    const double* row = theta + s * P.ndim;
+    const double Aamp = model_param(T, row, P.n_model + 0), le = model_param(T, row, P.n_model + 1);
+    const double lpp = model_param(T, row, P.n_model + 2), Pg = model_param(T, row, P.n_model + 3);
+    const double gamma = 1.0 / (2.0 * (lpp * lpp));          // gp.py:152
+    const double A2 = Aamp * Aamp, inv_le = 1.0 / le, inv_Pg = 1.0 / Pg;
+
+    // build this thread's tile                               gp.py:145-156, fit.py:8094-8096
+    double a[TT][TT];
+#pragma unroll
+    for (int r = 0; r < TT; ++r) {
+      const int i = r0 + r;
+#pragma unroll
+      for (int c = 0; c < TT; ++c) {
+        const int k = c0 + c;
+        double v = 0.0;
+#ifdef RVLP_GP_SKIP_BUILD
+        if (has_tile && i < N && k <= i) { v = (i == k) ? 10.0 + i : 0.001; } else
+#endif
+        if (has_tile && i < N && k <= i) {
+          const double tau = T.t[i] - T.t[k];
+          const double sn = sinpi(fabs(tau) * inv_Pg);
+          const double q = tau * inv_le;
+          v = A2 * exp(-gamma * (sn * sn) - 0.5 * (q * q));
+          if (i == k) v += T.e2[i] + sr[kHdr + P.n_inst + T.inst[i]];
+        } else if (has_tile && i == N && k < N) {
+          v = resid[k];
+        }
+        a[r][c] = v;
+      }
+    }
+    // Column sweep.  a_ik -= (a_ij / p)(a_kj) with p the pivot: no square roots anywhere
+    // (alpha_j^2 = a_Nj^2 / p, ln L_jj = ln(p) / 2).  Padding rows hold zeros; entries in
+    // columns >= N are never read, so only the "row / column already finished" masks remain and
+    // those are needed only while j runs through the tile's own rows / columns.
+    double quad = 0.0, prodm = 1.0;
+    int exsum = 0, par = 0;
+    // entry (i, k) only receives updates from columns j < k: the tile is final once j reaches its last column
+    const int jlast = has_tile ? c0 + TT - 1 : -1;           // last column this tile publishes
+    const int warp_last = __reduce_max_sync(0xffffffffu, jlast);
+    // Two-level column loop so that the column-within-tile index cj is a compile-time constant: the
+    // publishing threads then read a[r][cj] with static register indices (a run-time cj compiles to an
+    // indexed branch per column, which measured as ~40% of the sweep).
+    for (int Jt = 0; Jt < nt; ++Jt) {
+#pragma unroll
+    for (int cj = 0; cj < TT; ++cj) {
+      const int j = Jt * TT + cj;
+      if (j >= N) break;
+      double* col = colbuf + par * rows;
+      par ^= 1;
+      if (has_tile && J == Jt) {                              // owners publish column j
+#pragma unroll
+        for (int r = 0; r < TT; ++r) col[r0 + r] = a[r][cj];
+      }
+      __syncthreads();
+#ifndef RVLP_GP_ABL_NOSCALAR
+      if (tid == 0) {                                         // alpha_j^2 and ln L_jj
+        const double piv = col[j], aN = col[N];
+        quad = fma(aN * aN, 1.0 / piv, quad);
+        const int h = __double2hiint(piv);
+        if ((unsigned)(h - 0x00100000) < 0x7fe00000u) {
+          prodm *= __hiloint2double((h & 0x000fffff) | 0x3ff00000, __double2loint(piv));
+          exsum += (h >> 20) - 1023;
+        } else {
+          prodm *= piv;                                        // 0 / negative / NaN: let log() say so
+        }
+      }
+#endif
+#ifdef RVLP_GP_ABL_NOUPDATE
+      continue;
+#endif
+      if (j >= warp_last) continue;                           // every tile of this warp is final
+      if (j < jlast) {
+        const double ip = 1.0 / col[j];                        // inf / NaN when not positive definite
+        double Li[TT], Lk[TT];
+        const double2* ci = reinterpret_cast<const double2*>(col + r0);   // r0, c0 multiples of an even TT
+        const double2* ck = reinterpret_cast<const double2*>(col + c0);
+#pragma unroll
+        for (int r = 0; r < TT; r += 2) {
+          const double2 v = ci[r / 2];
+          Li[r] = v.x;
+          Li[r + 1] = v.y;
+        }
+#pragma unroll
+        for (int c = 0; c < TT; c += 2) {
+          const double2 v = ck[c / 2];
+          Lk[c] = v.x * ip;
+          Lk[c + 1] = v.y * ip;
+        }
+        if (j >= c0) {                                         // sweeping through this tile's own columns / rows
+#pragma unroll
+          for (int c = 0; c < TT; ++c)
+            if (c0 + c <= j) Lk[c] = 0.0;
+#pragma unroll
+          for (int r = 0; r < TT; ++r)
+            if (r0 + r <= j) Li[r] = 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < TT; ++r)
+#pragma unroll
+          for (int c = 0; c < TT; ++c) a[r][c] = fma(-Li[r], Lk[c], a[r][c]);
+      }
+    }
+    }
+    if (tid == 0) {
+      // sum_j ln L_jj = 1/2 ln prod piv_j
+      const double logdet = 0.5 * fma((double)exsum, 0.6931471805599453, log(prodm));
+      const double ll = -0.5 * quad - logdet - 0.5 * (double)N * kLog2Pi;
+      double r = ll + lp + lhp;                                // fit.py:7898-7900
+      r += P.jacobian;
+      r += P.renorm;
+      out[s] = r;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace rvlp

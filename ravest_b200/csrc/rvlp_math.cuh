@@ -341,8 +341,7 @@ RV_HD void kepler_stage_b(const StarterOut<W>& o, double e, int n64, double (&co
       sinE[i] = xor_hi(sn, sign[i]);
       dlast[i] = d;
     }
-    return;
-  }
+  } else {
 #pragma unroll
   for (int it = 0; it < (N64 >= 0 ? N64 : n64); ++it) {
 #pragma unroll
@@ -383,6 +382,7 @@ RV_HD void kepler_stage_b(const StarterOut<W>& o, double e, int n64, double (&co
     cosE[i] = c[i];
     sinE[i] = xor_hi(s[i], sign[i]);
     rinv[i] = rcp64(ffma(-e, c[i], 1.0));
+  }
   }
 }
 

@@ -311,7 +311,7 @@ def test_pickle_roundtrip_and_emcee_vectorize_contract(cuda):
 
 
 def test_gp_against_restatement(cuda):
-    """Config 5. GP parity is unpinned against tinygp (absent); the CUDA kernel is held to the
+    """Config 5. GP parity is unpinned against tinygp (absent); the CUDA kernels are held to the
     C / numpy restatements of SURVEY.md Appendix A.5."""
     from oracle import oracle_c, oracle_py
     from ravest_b200 import workloads
@@ -328,6 +328,40 @@ def test_gp_against_restatement(cuda):
         assert np.all(np.abs(got[:20][f2] - py[f2]) <= 1e-7 + 1e-11 * np.abs(py[f2]))
     x = dict(zip(post.free_params_names + post.free_hyperparams_names, theta[5]))
     assert abs(post.log_probability(x) - got[5]) == 0.0
+
+
+@pytest.mark.parametrize("N", [1, 2, 7, 43, 44, 87, 88, 131, 132, 175, 176, 200])
+def test_gp_every_tile_size_and_the_smem_kernel(cuda, N, monkeypatch):
+    """Register-tiled Cholesky at each tile size boundary (T = 2/4/6/8), the shared-memory kernel above
+    N = 175, and both kernels against each other at the same N."""
+    from oracle import oracle_c
+    from ravest_b200 import workloads
+    spec, theta = workloads.make_c5(n_samples=48, n_planets=1, n_epochs=N, seed=600 + N)
+    ref = oracle_c.OracleProblem(spec).logprob(theta)
+    got = _post(spec).log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
+    assert np.array_equal(np.isneginf(got), np.isneginf(ref))
+    fin = np.isfinite(ref)
+    assert fin.sum() > 30
+    assert np.all(np.abs(got[fin] - ref[fin]) <= 1e-7 + 1e-11 * np.abs(ref[fin])), np.abs(got[fin] - ref[fin]).max()
+    monkeypatch.setenv("RVLP_GP_SMEM_KERNEL", "1")
+    alt = _post(spec).log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
+    assert np.all(np.abs(alt[fin] - ref[fin]) <= 1e-7 + 1e-11 * np.abs(ref[fin]))
+
+
+def test_gp_not_positive_definite_and_bad_hyperparameters(cuda):
+    from ravest_b200 import workloads
+    spec, theta = workloads.make_c5(n_samples=16, n_planets=1, n_epochs=40)
+    names = workloads.free_names(spec) + list(spec["hyperparams"])
+    theta[0, names.index("gp_amp")] = 0.0            # gp.py:106-108 -> -inf
+    theta[1, names.index("gp_lambda_e")] = np.inf    # gp.py:99-101 -> -inf
+    theta[2, names.index("gp_period")] = np.nan      # not finite -> -inf
+    theta[3, names.index("jit_HARPS")] = -1.0        # fit.py:7857-7859
+    theta[4, names.index("K_b")] = -2.0              # invalid planet: mean model fails, fit.py:8022-8024, 8082
+    from oracle import oracle_c
+    got = _post(spec).log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
+    ref = oracle_c.OracleProblem(spec).logprob(theta)
+    assert np.all(np.isneginf(got[:5])) and np.array_equal(np.isneginf(got), np.isneginf(ref))
+    assert np.isfinite(got).sum() >= 8
 
 
 def test_fp64_peak_probe(cuda):
