@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <climits>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -221,10 +222,14 @@ static int launch_logprob(rvlp_ctx* c, const double* theta, int64_t S, double* o
                           cudaStream_t st) {
   if (S == 0) return RVLP_OK;
   int grid = 0;
-  const int64_t want = ((S + kG - 1) / kG + kWarps - 1) / kWarps;
-  int rc = grid_for(c->device, (const void*)logprob_kernel, c->smem_main, want, &grid);
+  int rc = grid_for(c->device, (const void*)logprob_kernel, c->smem_main, INT_MAX, &grid);   // full wave
   if (rc) return rc;
-  logprob_kernel<<<grid, kThreads, c->smem_main, st>>>(c->P, theta, S, out, ll, lp);
+  // samples per prologue batch: kG when every resident warp still gets a batch, else 1 (latency of small S)
+  int64_t per_warp = S / ((int64_t)grid * kWarps);
+  const int nb = (int)(per_warp >= kG ? kG : (per_warp < 1 ? 1 : per_warp));
+  const int64_t want = ((S + nb - 1) / nb + kWarps - 1) / kWarps;
+  if (want < grid) grid = (int)want;
+  logprob_kernel<<<grid, kThreads, c->smem_main, st>>>(c->P, theta, S, out, ll, lp, nb);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return RVLP_OK;

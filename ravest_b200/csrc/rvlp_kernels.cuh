@@ -185,9 +185,9 @@ __device__ __forceinline__ double model_param(const Tables& T, const double* row
 // Phase B: one lane per sample: jitter check, gamma / jitter^2, priors in order.
 __device__ __forceinline__ void sample_prologue(const DevProblem& P, const Tables& T, const double* theta,
                                                 int64_t s0, int64_t S, double* scratch, int rec, int lane,
-                                                bool with_priors) {
+                                                bool with_priors, int nb = kG) {
   const int npl = P.n_planets;
-  for (int task = lane; task < kG * npl; task += 32) {
+  for (int task = lane; task < nb * npl; task += 32) {
     const int g = task / npl, k = task - g * npl;
     const int64_t s = s0 + g;
     if (s >= S) continue;
@@ -206,7 +206,7 @@ __device__ __forceinline__ void sample_prologue(const DevProblem& P, const Table
     pr[15] = d.invalid ? 1.0 : 0.0;
   }
   __syncwarp();
-  if (lane < kG && s0 + lane < S) {
+  if (lane < nb && s0 + lane < S) {
     const int g = lane;
     const double* row = theta + (s0 + g) * P.ndim;
     double* sr = scratch + g * rec;
@@ -438,7 +438,7 @@ __device__ __forceinline__ void sample_chi_pipelined(const DevProblem& P, const 
 // ------------------------------------------------------------------ K1: log-probability
 __global__ void __launch_bounds__(kThreads, RVLP_MIN_BLOCKS)
 logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double* __restrict__ out,
-               double* __restrict__ ll_out, double* __restrict__ lp_out) {
+               double* __restrict__ ll_out, double* __restrict__ lp_out, int nb) {
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = smem_layout(P);
   stage_problem(P, L, smem);
@@ -446,16 +446,18 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
   double* scratch = reinterpret_cast<double*>(smem + L.off_scratch) + warp * kG * rec;
-  const int64_t n_batches = (S + kG - 1) / kG;
+  // nb = samples per prologue batch (1..kG): small launches use 1 so that every warp gets a sample;
+  // the bits of a sample's result do not depend on it.
+  const int64_t n_batches = (S + nb - 1) / nb;
   const int64_t gw = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
 #if RVLP_STAGGER_NS > 0
   if ((warp >> 2) & 1) __nanosleep(RVLP_STAGGER_NS);
 #endif
 
   for (int64_t b = gw; b < n_batches; b += nw) {
-    const int64_t s0 = b * kG;
-    sample_prologue(P, T, theta, s0, S, scratch, rec, lane, true);
-    for (int g = 0; g < kG; ++g) {
+    const int64_t s0 = b * nb;
+    sample_prologue(P, T, theta, s0, S, scratch, rec, lane, true, nb);
+    for (int g = 0; g < nb; ++g) {
       const int64_t s = s0 + g;
       if (s >= S) break;
       const double* sr = scratch + g * rec;
