@@ -79,7 +79,7 @@ struct rvlp_ctx {
   void* d_src_const = nullptr;
   void* d_priors = nullptr;
   void* d_epochs = nullptr;
-  int smem_main = 0, smem_gp = 0, smem_gp_tiled = 0, gp_tile = 0;
+  int smem_main = 0, smem_gp = 0, smem_gp_tiled = 0, smem_gp_blocked = 0, gp_tile = 0;
   int max_smem = 0;
   // host-buffer path
   double* h_theta = nullptr;
@@ -192,10 +192,15 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     c->gp_tile = gp_tile_for(P.n_epochs);
     c->smem_gp_tiled = gp_tiled_smem(P, L).total;
+    c->smem_gp_blocked = c->gp_tile ? gp_blocked_smem(P, L, c->gp_tile).total : 0;
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CTX_TRY(cudaFuncSetAttribute(gp_logprob_blocked_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CTX_TRY(cudaFuncSetAttribute(gp_logprob_blocked_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CTX_TRY(cudaFuncSetAttribute(gp_logprob_blocked_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CTX_TRY(cudaFuncSetAttribute(gp_logprob_blocked_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   }
   CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 #undef CTX_TRY
@@ -324,13 +329,26 @@ int rvlp_gp_logprob_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
   int grid = 0;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
+  // RVLP_GP_KERNEL=smem|column selects the older kernels (kept for cross-checks in the tests)
+  const char* which = getenv("RVLP_GP_KERNEL");
+  const bool use_smem = which && !strcmp(which, "smem");
+  // measured on B200 (tools/gp_time.py): the panel kernel wins at T = 2 and 6, the column sweep at T = 4 and 8
+  bool use_column = c->gp_tile == 4 || c->gp_tile == 8;
+  if (which && !strcmp(which, "column")) use_column = true;
+  if (which && !strcmp(which, "blocked")) use_column = false;
 #define RVLP_GP_TILED(TT)                                                                                   \
   case TT:                                                                                                  \
-    rc = grid_for(c->device, (const void*)gp_logprob_tiled_kernel<TT>, c->smem_gp_tiled, S, &grid);         \
-    if (rc) return rc;                                                                                      \
-    gp_logprob_tiled_kernel<TT><<<grid, kThreads, c->smem_gp_tiled, st>>>(c->P, theta_dev, S, out_dev);     \
+    if (use_column) {                                                                                       \
+      rc = grid_for(c->device, (const void*)gp_logprob_tiled_kernel<TT>, c->smem_gp_tiled, S, &grid);       \
+      if (rc) return rc;                                                                                    \
+      gp_logprob_tiled_kernel<TT><<<grid, kThreads, c->smem_gp_tiled, st>>>(c->P, theta_dev, S, out_dev);   \
+    } else {                                                                                                \
+      rc = grid_for(c->device, (const void*)gp_logprob_blocked_kernel<TT>, c->smem_gp_blocked, S, &grid);   \
+      if (rc) return rc;                                                                                    \
+      gp_logprob_blocked_kernel<TT><<<grid, kThreads, c->smem_gp_blocked, st>>>(c->P, theta_dev, S, out_dev); \
+    }                                                                                                       \
     break;
-  switch (getenv("RVLP_GP_SMEM_KERNEL") ? 0 : c->gp_tile) {
+  switch (use_smem ? 0 : c->gp_tile) {
     RVLP_GP_TILED(2)
     RVLP_GP_TILED(4)
     RVLP_GP_TILED(6)

@@ -343,4 +343,219 @@ gp_logprob_tiled_kernel(DevProblem P, const double* __restrict__ theta, int64_t 
   }
 }
 
+// ------------------------------------------------------------------ K3, blocked (panel) version
+// Same register tiling, but the sweep advances one PANEL of TT columns per step instead of one column:
+//   1. the diagonal tile's owner factorises its TT x TT tile in registers and publishes L_d and 1/diag;
+//   2. the tiles below it solve X L_d^T = A in registers (TRSM) and publish X, stored k-major;
+//   3. every trailing tile subtracts P_I P_J^T: TT rank-1 updates with no barrier, mask or division between.
+// Two barriers per panel (N/TT panels) instead of one per column.  The residual row N rides along as before:
+// after step 2 its entries are alpha_j; ln L_jj comes from the pivots.  Deterministic: fixed tile ownership,
+// fixed summation order, fixed-order final reduction.
+struct GpBlockedSmem { int off_resid, off_d, off_p, off_red, total; };
+__host__ __device__ inline GpBlockedSmem gp_blocked_smem(const DevProblem& P, const SmemLayout& L, int TT) {
+  GpBlockedSmem G;
+  int o = (L.total + 15) & ~15;
+  const int nt = (P.n_epochs + 1 + TT - 1) / TT;
+  G.off_resid = o; o += ((P.n_epochs + 2) & ~1) * 8;
+  G.off_d = o; o += (TT * TT + TT) * 8;
+  o = (o + 15) & ~15;
+  G.off_p = o; o += nt * TT * TT * 8;
+  G.off_red = o; o += 2 * kThreads * 8;
+  G.total = o;
+  return G;
+}
+
+template <int TT>
+__global__ void __launch_bounds__(kThreads, (TT >= 8 ? 1 : 2))
+gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout L = smem_layout(P);
+  const GpBlockedSmem G = gp_blocked_smem(P, L, TT);
+  stage_problem(P, L, smem);
+  const Tables T = tables_of(L, smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
+  double* scratch = reinterpret_cast<double*>(smem + L.off_scratch);
+  double* resid = reinterpret_cast<double*>(smem + G.off_resid);
+  double* dbuf = reinterpret_cast<double*>(smem + G.off_d);
+  double* pbuf = reinterpret_cast<double*>(smem + G.off_p);
+  double* red = reinterpret_cast<double*>(smem + G.off_red);
+  const int N = P.n_epochs;
+  const int nt = (N + 1 + TT - 1) / TT;          // tile rows (incl. the residual row N)
+  const int ntc = (N + TT - 1) / TT;             // panels (columns 0..N-1)
+  int J = 0, rem = tid;
+  while (J < nt && rem >= nt - J) { rem -= nt - J; ++J; }
+  const int I = J + rem;
+  const bool has_tile = J < nt;
+  const int r0 = I * TT, c0 = J * TT;
+  const int IN = N / TT, rN = N - IN * TT;       // where the residual row lives
+
+  for (int64_t s = blockIdx.x; s < S; s += gridDim.x) {
+    if (warp == 0) sample_prologue(P, T, theta, s, s + 1, scratch, rec, lane, true, 1);
+    __syncthreads();
+    const double* sr = scratch;
+    const int flags = __double2loint(sr[1]);
+    const double lp = sr[0], lhp = sr[4];
+    if (flags & (F_JIT | F_HYPER | F_PRIOR)) {               // fit.py:7857-7886
+      if (tid == 0) out[s] = -INFINITY;
+      __syncthreads();
+      continue;
+    }
+    int nonfinite = (flags & F_PLANET) ? 1 : 0;              // fit.py:8022-8024
+    if (!nonfinite) {
+      for (int i = tid; i < N; i += kThreads) {              // residual v - mean, fit.py:7994-8043, 8059
+        double tt[1] = {T.t[i]}, rv[1];
+        model_rv<1>(P, sr, tt, rv, -1, true);
+        const double mean = rv[0] + sr[kHdr + T.inst[i]];
+        if (!(fabs(mean) <= 1.79769313486231570e308)) nonfinite = 1;
+        resid[i] = T.v[i] - mean;
+      }
+    }
+    if (__syncthreads_or(nonfinite)) {                       // fit.py:8082-8083
+      if (tid == 0) {
+        double r = -INFINITY + lp + lhp;
+        r += P.jacobian;
+        r += P.renorm;
+        out[s] = r;
+      }
+      __syncthreads();
+      continue;
+    }
+    const double* row = theta + s * P.ndim;
+    const double Aamp = model_param(T, row, P.n_model + 0), le = model_param(T, row, P.n_model + 1);
+    const double lpp = model_param(T, row, P.n_model + 2), Pg = model_param(T, row, P.n_model + 3);
+    const double gamma = 1.0 / (2.0 * (lpp * lpp));          // gp.py:152
+    const double A2 = Aamp * Aamp, inv_le = 1.0 / le, inv_Pg = 1.0 / Pg;
+
+    double a[TT][TT];                                         // gp.py:145-156, fit.py:8094-8096
+#pragma unroll
+    for (int r = 0; r < TT; ++r) {
+      const int i = r0 + r;
+#pragma unroll
+      for (int c = 0; c < TT; ++c) {
+        const int k = c0 + c;
+        double v = 0.0;
+        if (has_tile && i < N && k <= i) {
+          const double tau = T.t[i] - T.t[k];
+          const double sn = sinpi(fabs(tau) * inv_Pg);
+          const double q = tau * inv_le;
+          v = A2 * exp(-gamma * (sn * sn) - 0.5 * (q * q));
+          if (i == k) v += T.e2[i] + sr[kHdr + P.n_inst + T.inst[i]];
+        } else if (has_tile && i == N && k < N) {
+          v = resid[k];
+        }
+        a[r][c] = v;
+      }
+    }
+    double quad = 0.0, prodm = 1.0;      // partial alpha.alpha and pivot product of THIS thread
+    int exsum = 0;
+    for (int Jt = 0; Jt < ntc; ++Jt) {
+      // ---- 1. diagonal tile: unblocked Cholesky in registers
+      if (has_tile && I == Jt && J == Jt) {
+        double invd[TT];
+#pragma unroll
+        for (int c = 0; c < TT; ++c) {
+          const bool valid = c0 + c < N;                       // columns >= N: identity (no-op) column
+          const double d = a[c][c];
+          const double inv = valid ? rsqrt(d) : 1.0;           // NaN when not positive definite (as jax)
+          invd[c] = inv;
+          a[c][c] = valid ? d * inv : 1.0;
+          if (valid) {
+            const int h = __double2hiint(d);
+            if ((unsigned)(h - 0x00100000) < 0x7fe00000u) {
+              prodm *= __hiloint2double((h & 0x000fffff) | 0x3ff00000, __double2loint(d));
+              exsum += (h >> 20) - 1023;
+            } else {
+              prodm *= d;                                      // 0 / negative / NaN: let log() say so
+            }
+          }
+#pragma unroll
+          for (int r = c + 1; r < TT; ++r) a[r][c] = valid ? a[r][c] * inv : 0.0;
+#pragma unroll
+          for (int r = c + 1; r < TT; ++r)
+#pragma unroll
+            for (int k = c + 1; k <= r; ++k) a[r][k] = fma(-a[r][c], a[k][c], a[r][k]);
+        }
+        if (IN == Jt) {                                        // the residual row sits in this tile
+#pragma unroll
+          for (int r = 0; r < TT; ++r)
+            if (r == rN) {
+#pragma unroll
+              for (int c = 0; c < TT; ++c)
+                if (c < r) quad = fma(a[r][c], a[r][c], quad);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < TT; ++r)
+#pragma unroll
+          for (int c = 0; c < TT; ++c) dbuf[r * TT + c] = (c <= r) ? a[r][c] : 0.0;
+#pragma unroll
+        for (int c = 0; c < TT; ++c) dbuf[TT * TT + c] = invd[c];
+      }
+      __syncthreads();
+      // ---- 2. panel tiles: X L_d^T = A, publish X k-major
+      if (has_tile && J == Jt && I > Jt) {
+#pragma unroll
+        for (int c = 0; c < TT; ++c) {
+          const double inv = dbuf[TT * TT + c];
+#pragma unroll
+          for (int r = 0; r < TT; ++r) {
+            double x = a[r][c];
+#pragma unroll
+            for (int k = 0; k < c; ++k) x = fma(-a[r][k], dbuf[c * TT + k], x);
+            a[r][c] = x * inv;
+          }
+        }
+        if (I == IN) {                                         // alpha_j for this panel's columns
+#pragma unroll
+          for (int r = 0; r < TT; ++r)
+            if (r == rN) {
+#pragma unroll
+              for (int c = 0; c < TT; ++c) quad = fma(a[r][c], a[r][c], quad);
+            }
+        }
+        double* pb = pbuf + I * TT * TT;
+#pragma unroll
+        for (int k = 0; k < TT; ++k)
+#pragma unroll
+          for (int r = 0; r < TT; ++r) pb[k * TT + r] = a[r][k];
+      }
+      __syncthreads();
+      // ---- 3. trailing tiles: a -= P_I P_J^T
+      if (has_tile && J > Jt) {
+        const double2* pi = reinterpret_cast<const double2*>(pbuf + I * TT * TT);
+        const double2* pj = reinterpret_cast<const double2*>(pbuf + J * TT * TT);
+#pragma unroll
+        for (int k = 0; k < TT; ++k) {
+          double Li[TT], Lk[TT];
+#pragma unroll
+          for (int r = 0; r < TT; r += 2) {
+            const double2 u = pi[(k * TT + r) / 2], w = pj[(k * TT + r) / 2];
+            Li[r] = u.x; Li[r + 1] = u.y;
+            Lk[r] = w.x; Lk[r + 1] = w.y;
+          }
+#pragma unroll
+          for (int r = 0; r < TT; ++r)
+#pragma unroll
+            for (int c = 0; c < TT; ++c) a[r][c] = fma(-Li[r], Lk[c], a[r][c]);
+        }
+      }
+    }
+    // fixed-order reduction of the per-thread partials (only a few threads hold non-trivial ones)
+    red[tid] = quad;
+    red[kThreads + tid] = 0.5 * fma((double)exsum, 0.6931471805599453, log(prodm));   // sum ln L_jj of this thread
+    __syncthreads();
+    if (tid == 0) {
+      double q = 0.0, logdet = 0.0;
+      for (int t = 0; t < kThreads; ++t) { q += red[t]; logdet += red[kThreads + t]; }
+      const double ll = -0.5 * q - logdet - 0.5 * (double)N * kLog2Pi;
+      double r = ll + lp + lhp;                                // fit.py:7898-7900
+      r += P.jacobian;
+      r += P.renorm;
+      out[s] = r;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace rvlp

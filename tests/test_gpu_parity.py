@@ -343,9 +343,10 @@ def test_gp_every_tile_size_and_the_smem_kernel(cuda, N, monkeypatch):
     fin = np.isfinite(ref)
     assert fin.sum() > 30
     assert np.all(np.abs(got[fin] - ref[fin]) <= 1e-7 + 1e-11 * np.abs(ref[fin])), np.abs(got[fin] - ref[fin]).max()
-    monkeypatch.setenv("RVLP_GP_SMEM_KERNEL", "1")
-    alt = _post(spec).log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
-    assert np.all(np.abs(alt[fin] - ref[fin]) <= 1e-7 + 1e-11 * np.abs(ref[fin]))
+    for which in ("smem", "column", "blocked"):   # every kernel variant against the same oracle
+        monkeypatch.setenv("RVLP_GP_KERNEL", which)
+        alt = _post(spec).log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
+        assert np.all(np.abs(alt[fin] - ref[fin]) <= 1e-7 + 1e-11 * np.abs(ref[fin])), which
 
 
 def test_gp_not_positive_definite_and_bad_hyperparameters(cuda):
