@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <climits>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -63,6 +64,20 @@ int grid_for(int device, const void* kernel, int smem_bytes, int64_t want_blocks
   return RVLP_OK;
 }
 
+// Per-device one-time upload of the sin/cos grid table (host libm values).
+int ensure_tables(int device) {
+  static std::atomic<uint64_t> done{0};
+  if (device < 64 && (done.load() >> device) & 1) return RVLP_OK;
+  std::vector<double> tab(2 * (size_t)kTabN);
+  for (int j = 0; j < kTabN; ++j) {
+    tab[2 * j] = sin(j / 512.0);
+    tab[2 * j + 1] = cos(j / 512.0);
+  }
+  CUDA_TRY(cudaMemcpyToSymbol(kSinCosTabDev, tab.data(), sizeof(double) * tab.size()));
+  if (device < 64) done.fetch_or(1ull << device);
+  return RVLP_OK;
+}
+
 int simple_grid(int64_t n) {
   int64_t g = (n + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
@@ -87,7 +102,8 @@ struct rvlp_ctx {
   double* d_theta = nullptr;
   double* d_out = nullptr;
   int64_t cap_samples = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;    // host-buffer path: chunks alternate between two streams so that
+  cudaStream_t stream2 = nullptr;   // the H2D copy of chunk i+1 overlaps the kernel of chunk i
 };
 
 extern "C" {
@@ -125,6 +141,7 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
   CUDA_TRY(cudaGetDeviceCount(&ndev));
   if (device < 0 || device >= ndev) return fail(RVLP_EINVAL, "device %d not present (%d visible)", device, ndev);
   DeviceGuard guard(device);
+  if (int rc = ensure_tables(device)) return rc;
 
   rvlp_ctx* c = new rvlp_ctx();
   c->device = device;
@@ -203,6 +220,7 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_blocked_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   }
   CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CTX_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
 #undef CTX_TRY
   *out = c;
   return RVLP_OK;
@@ -220,6 +238,7 @@ void rvlp_ctx_destroy(rvlp_ctx* c) {
   if (c->h_theta) cudaFreeHost(c->h_theta);
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   delete c;
 }
 
@@ -284,21 +303,24 @@ int rvlp_logprob_batch_host(rvlp_ctx* c, const double* theta_host, int64_t S, do
   const bool in_pinned = is_pinned(theta_host), out_pinned = is_pinned(out_host);
   const double* src = in_pinned ? theta_host : c->h_theta;
   double* dst = out_pinned ? out_host : c->h_out;
-  // chunked so that the H2D of chunk i+1 (and the staging memcpy) overlaps the kernel of chunk i
+  // chunked, chunks alternating between two streams: the H2D of chunk i+1 (and the staging memcpy) overlaps
+  // the kernel of chunk i, the D2H of chunk i overlaps the kernel of chunk i+1
   const int64_t chunk = S > (1 << 16) ? (S + 7) / 8 : S;
-  for (int64_t s0 = 0; s0 < S; s0 += chunk) {
+  int ci = 0;
+  for (int64_t s0 = 0; s0 < S; s0 += chunk, ++ci) {
+    cudaStream_t st = (ci & 1) ? c->stream2 : c->stream;
     const int64_t n = (S - s0 < chunk) ? S - s0 : chunk;
     const size_t off = (size_t)s0 * (size_t)c->P.ndim;
     const size_t nbytes = sizeof(double) * (size_t)n * (size_t)c->P.ndim;
     if (!in_pinned) memcpy(c->h_theta + off, theta_host + off, nbytes);
-    CUDA_TRY(cudaMemcpyAsync(c->d_theta + off, src + off, nbytes, cudaMemcpyHostToDevice, c->stream));
-    int rc = c->P.n_hyper ? rvlp_gp_logprob_batch(c, c->d_theta + off, n, c->d_out + s0, c->stream)
-                          : launch_logprob(c, c->d_theta + off, n, c->d_out + s0, nullptr, nullptr, c->stream);
+    CUDA_TRY(cudaMemcpyAsync(c->d_theta + off, src + off, nbytes, cudaMemcpyHostToDevice, st));
+    int rc = c->P.n_hyper ? rvlp_gp_logprob_batch(c, c->d_theta + off, n, c->d_out + s0, st)
+                          : launch_logprob(c, c->d_theta + off, n, c->d_out + s0, nullptr, nullptr, st);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(dst + s0, c->d_out + s0, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost,
-                             c->stream));
+    CUDA_TRY(cudaMemcpyAsync(dst + s0, c->d_out + s0, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
   }
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream2));
   if (!out_pinned) memcpy(out_host, c->h_out, sizeof(double) * (size_t)S);
   return RVLP_OK;
 }
@@ -369,6 +391,7 @@ int rvlp_kepler_rv(const double* M_dev, int64_t n, double e, double K, double w,
   if (n < 0 || (n > 0 && (!M_dev || !rv_dev))) return fail(RVLP_EINVAL, "bad arguments");
   if (n == 0) return RVLP_OK;
   DeviceGuard guard(device);
+  if (int rc = ensure_tables(device)) return rc;
   kepler_rv_kernel<<<simple_grid(n), 256, 0, (cudaStream_t)stream>>>(M_dev, n, e, K, w, rv_dev);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
@@ -389,6 +412,7 @@ int rvlp_planet_rv(int32_t par, const double* p5, const double* t_dev, int64_t n
   if (n < 0 || (n > 0 && (!t_dev || !rv_dev))) return fail(RVLP_EINVAL, "bad arguments");
   if (n == 0) return RVLP_OK;
   DeviceGuard guard(device);
+  if (int rc = ensure_tables(device)) return rc;
   planet_rv_kernel<<<simple_grid(n), 256, 0, (cudaStream_t)stream>>>(d, t_dev, n, rv_dev, accumulate);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());

@@ -34,9 +34,10 @@ constexpr int kWarps = kThreads / 32;
 #endif
 // Bit mask: software-pipelined sample evaluation (see sample_chi_pipelined) for samples whose planets all
 // take the lite plan (bit 0) / all have e <= 0.97 (bit 1).  Measured on B200 (profiles/r01_sweep5/6.log):
-// pipelining helps the mixed-plan high-e workload (+8% on config 4) and costs 9% on the all-lite config 3.
+// with the polynomial sincos pipelining helped the mixed-plan high-e workload (+8% on config 4) and cost 9% on
+// the all-lite config 3; with the table-based sincos (r01_sweep7.log) the plain loop wins on both: default off.
 #ifndef RVLP_PIPELINE
-#define RVLP_PIPELINE 2
+#define RVLP_PIPELINE 0
 #endif
 #ifndef RVLP_STAGGER_NS        // experiment: delay every other warp pair at kernel start
 #define RVLP_STAGGER_NS 0

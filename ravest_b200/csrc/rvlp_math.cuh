@@ -97,6 +97,28 @@ static const double kCoefHost[22] = RV_SINCOS_COEFS;
 #define RVK(i) kCoefHost[i]
 #endif
 
+// sin / cos at the grid points j / 512, j = 0 .. kTabN-1 (covers [0, pi]): the fp64 stage looks up
+// the grid point nearest to E0 and rotates by the (exactly representable) remainder |E0 - j/512| <= 2^-10,
+// which needs only a cubic / quartic series - 10 fp64 operations instead of the 19 of the polynomial
+// kernels, and no quadrant logic.  Filled once per device from host libm (rvlp_capi.cu) / on first use (host).
+constexpr int kTabN = 1610;
+#ifndef RVLP_SINCOS_TABLE
+#define RVLP_SINCOS_TABLE 1
+#endif
+#if defined(__CUDACC__)
+__device__ double2 kSinCosTabDev[kTabN];
+#endif
+struct SinCosPair { double s, c; };
+inline const SinCosPair* sincos_table_host() {
+  static SinCosPair tab[kTabN];
+  static bool init = false;
+  if (!init) {
+    for (int j = 0; j < kTabN; ++j) { tab[j].s = sin(j / 512.0); tab[j].c = cos(j / 512.0); }
+    init = true;
+  }
+  return tab;
+}
+
 // ---------------------------------------------------------------- reciprocals
 RV_HD double rcp64(double x) {
 #if defined(__CUDA_ARCH__)
@@ -189,6 +211,29 @@ RV_HD void sincos_0pi(double x, float xf, double& s, double& c) {
   const double c0 = swap ? sr : cr;
   s = xor_hi(s0, q2 ? (int)0x80000000 : 0);
   c = xor_hi(c0, q1 ? (int)0x80000000 : 0);
+}
+
+// sin / cos of a float-exact E0 in [0, pi] by table + rotation (see kSinCosTabDev).
+RV_HD void sincos_0pi_table(float E0f, double& s, double& c) {
+  const float t = ffmaf(E0f, 512.0f, 12582912.0f);       // 1.5 * 2^23 + rint(512 E0)
+  const float jf = t - 12582912.0f;
+  const float ebf = ffmaf(jf, -0.001953125f, E0f);        // E0 - j / 512, exact
+  const double eb = (double)ebf;
+#if defined(__CUDA_ARCH__)
+  const int j = __float_as_int(t) - 0x4b400000;
+  const double2 sc = __ldg(&kSinCosTabDev[j]);
+  const double sa = sc.x, ca = sc.y;
+#else
+  const int j = (int)jf;
+  const SinCosPair sc = sincos_table_host()[j];
+  const double sa = sc.s, ca = sc.c;
+#endif
+  // |eb| <= 2^-10:  sin eb = eb - eb^3/6 (+ 7e-18),  cos eb - 1 = -eb^2/2 + eb^4/24 (- 1e-21)
+  const double z = eb * eb;
+  const double sb = ffma(eb * z, RVK(21), eb);
+  const double cb1 = z * ffma(z, RVK(20), -0.5);
+  s = ffma(sa, cb1, ffma(ca, sb, sa));
+  c = ffma(ca, cb1, ffma(-sa, sb, ca));
 }
 
 // Reduce a mean anomaly to m in [0, pi] and a sign bit:  M = 2 pi k + sign * m.
@@ -319,7 +364,11 @@ RV_HD void kepler_stage_b(const StarterOut<W>& o, double e, int n64, double (&co
 #pragma unroll
   for (int i = 0; i < W; ++i) {
     E[i] = (double)o.Ef[i];
+#if RVLP_SINCOS_TABLE
+    sincos_0pi_table(o.Ef[i], s[i], c[i]);
+#else
     sincos_0pi(E[i], o.Ef[i], s[i], c[i]);
+#endif
     dlast[i] = 0.0;
   }
   if (N64 == 0) {

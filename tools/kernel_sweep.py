@@ -12,12 +12,13 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VDIR = os.path.join(ROOT, "build_variants")
 VARIANTS = {
-    "base": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=2"],
-    "stag100": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=2", "-DRVLP_STAGGER_NS=100"],
-    "stag250": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=2", "-DRVLP_STAGGER_NS=250"],
-    "stag600": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=2", "-DRVLP_STAGGER_NS=600"],
-    "stag2000": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=2", "-DRVLP_STAGGER_NS=2000"],
-    "pipe_wp2": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=2", "-DRVLP_PIPELINE=1", "-DRVLP_WP=2"],
+    "tab0_w4_mb2": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=2", "-DRVLP_SINCOS_TABLE=0"],
+    "tab1_w4_mb2": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=2", "-DRVLP_SINCOS_TABLE=1"],
+    "tab1_w4_mb2_pipe3": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=2", "-DRVLP_SINCOS_TABLE=1", "-DRVLP_PIPELINE=3"],
+    "tab1_w4_mb2_pipe0": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=2", "-DRVLP_SINCOS_TABLE=1", "-DRVLP_PIPELINE=0"],
+    "tab1_w3_mb2": ["-DRVLP_W=3", "-DRVLP_MIN_BLOCKS=2", "-DRVLP_SINCOS_TABLE=1"],
+    "tab1_w2_mb3": ["-DRVLP_W=2", "-DRVLP_MIN_BLOCKS=3", "-DRVLP_SINCOS_TABLE=1"],
+    "tab1_w6_mb1": ["-DRVLP_W=6", "-DRVLP_MIN_BLOCKS=1", "-DRVLP_SINCOS_TABLE=1", "-DRVLP_WP=2"],
 }
 
 CHILD = r"""
