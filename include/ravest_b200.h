@@ -141,10 +141,58 @@ int rvlp_rv_batch(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples,
                   const double* times_dev, int64_t n_times, int32_t component,
                   double* out_dev, void* stream);
 
+/* rvlp_rv_batch with per-call parameter overrides: Fitter._resolve_freeze_params +
+ * _calculate_rv_planet_from_samples (fit.py:2586-2688, 2726-2751: `params.update(resolved_freeze)` for every
+ * sample).  frozen_index[i] (HOST array) is a model-parameter number as defined at rvlp_desc, frozen_value[i]
+ * the value every sample uses instead of its own; n_frozen <= RVLP_MAX_FROZEN. */
+#define RVLP_MAX_FROZEN 16
+int rvlp_rv_batch_frozen(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples,
+                         const double* times_dev, int64_t n_times, int32_t component,
+                         int32_t n_frozen, const int32_t* frozen_index, const double* frozen_value,
+                         double* out_dev, void* stream);
+
+/* Replaces the per-row checks of Fitter.generate_initial_walker_positions_{random,around_point} and
+ * Fitter.run_mcmc (fit.py:692-725, 884-902, 1048-1062; GPFitter twins fit.py:4500-4540, 4750-4790, 4950-4990):
+ * _validate_astrophysical_validity (fit.py:260-293) followed by "log-prior of the converted parameters is
+ * finite".  status_dev [S] gets 0 for a usable row, else an OR of the bits below; logprior_dev /
+ * loghyperprior_dev [S] (either may be NULL) get LogPrior / log_hyperprior. */
+enum {
+  RVLP_WALKER_NONFINITE = 1,    /* some free or fixed parameter is NaN / inf        fit.py:262-265      */
+  RVLP_WALKER_PLANET = 2,       /* conversion or param.py:88-105 validity failed    fit.py:268-276      */
+  RVLP_WALKER_JITTER = 4,       /* jit_<inst> < 0                                   fit.py:289-293      */
+  RVLP_WALKER_PRIOR = 8,        /* log-prior not finite                             fit.py:717-720      */
+  RVLP_WALKER_HYPER = 16,       /* GP hyperparameter not finite or <= 0             gp.py:82-108        */
+  RVLP_WALKER_HYPERPRIOR = 32   /* log-hyperprior not finite                        fit.py:4534-4537    */
+};
+int rvlp_walker_check_batch(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples,
+                            int32_t* status_dev, double* logprior_dev, double* loghyperprior_dev,
+                            void* stream);
+
 /* Replaces GPLogPosterior.log_probability (fit.py:7836-7901), batched; requires a descriptor
  * with n_hyper == 4. theta columns: free_params_names + free_hyperparams_names (fit.py:4978). */
 int rvlp_gp_logprob_batch(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples,
                           double* out_dev, void* stream);
+
+/* Replaces the per-sample loops of GPFitter's posterior predictions (fit.py:6383-6414, 7494-7554:
+ * `gp.condition(y = vel - gamma - planets - trend, X_test = times)` -> conditional mean) and
+ * GPFitter._compute_gp_chi2 (fit.py:5386-5429).  mean_dev is [S, n_times] row-major (may be NULL with
+ * n_times == 0), chi2_dev [S] (may be NULL).  Rows whose planet parameters or hyperparameters are invalid are
+ * NaN (the reference raises there).  Requires n_hyper == 4. */
+int rvlp_gp_predict_batch(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples,
+                          const double* times_dev, int64_t n_times, double* mean_dev,
+                          double* chi2_dev, void* stream);
+
+/* Replaces `np.percentile(matrix, q, axis=0)` on the per-sample RV matrices (fit.py:2239-2240, 2493-2495;
+ * GP twins fit.py:6440-6450): matrix_dev is [n_rows, n_cols] row-major (the layout rvlp_rv_batch writes),
+ * q_percent a HOST array of n_q <= RVLP_MAX_PERCENTILES percentiles in [0, 100], out_dev [n_q, n_cols].
+ * numpy's default "linear" method, bit-exact (exact order statistics + numpy's _lerp arithmetic); a column
+ * holding a NaN gives NaN, as numpy.  workspace_dev: caller-owned scratch of at least
+ * rvlp_percentile_workspace_bytes(n_cols, n_q) bytes, 256-byte aligned. */
+#define RVLP_MAX_PERCENTILES 8
+int64_t rvlp_percentile_workspace_bytes(int64_t n_cols, int32_t n_q);
+int rvlp_percentile_columns(const double* matrix_dev, int64_t n_rows, int64_t n_cols,
+                            const double* q_percent, int32_t n_q, double* out_dev,
+                            void* workspace_dev, int64_t workspace_bytes, int device, void* stream);
 
 /* Replaces ravest.model._compute_rv / _njit_kepler_rv (model.py:173-243) for a batch of
  * default-space orbits: M_dev [n] mean anomalies, one (e, K, w) triple -> rv_dev [n]. */

@@ -373,12 +373,15 @@ class Problem:
     def build_params(self, row) -> dict:
         return self.fixed | dict(zip(self.free_names, (float(x) for x in row)))
 
-    def rv_matrix(self, theta: np.ndarray, times: np.ndarray, component: str) -> np.ndarray:
-        """fit.py:2726-2824 — component: planet letter, 'trend' or 'total'."""
+    def rv_matrix(self, theta: np.ndarray, times: np.ndarray, component: str, frozen: dict | None = None) -> np.ndarray:
+        """fit.py:2726-2824 — component: planet letter, 'trend' or 'total'; `frozen` is the resolved
+        freeze_params mapping applied to every sample (`params.update(resolved_freeze)`, fit.py:2743-2745)."""
         theta = np.atleast_2d(theta)
         out = np.zeros((theta.shape[0], len(times)))
         for i, row in enumerate(theta):
             p = self.build_params(row)
+            if frozen:
+                p.update(frozen)
             acc = np.zeros(len(times))
             if component in ("trend", "total"):
                 acc = acc + trend_rv(p["gd"], p["gdd"], times, self.t0)
@@ -387,3 +390,60 @@ class Problem:
                     acc = acc + planet_rv(self.parameterisation, {q: p[f"{q}_{L}"] for q in self.pars}, times)
             out[i] = acc
         return out
+
+    # ------------------------------------------------------------------ walker checks (row f-3)
+    def walker_stage(self, row) -> tuple[str, float | None]:
+        """What fit.py:1048-1062 (and the retry loops fit.py:692-725, 884-902) decide for one candidate row:
+        'astro' = _validate_astrophysical_validity raised (fit.py:260-293), 'prior' = non-finite log-prior,
+        'ok' otherwise (with the log-prior)."""
+        free = dict(zip(self.free_names, (float(x) for x in row)))
+        allp = self.fixed | free
+        if any(not np.isfinite(v) for v in allp.values()):                 # fit.py:262-265
+            return "astro", None
+        for L in self.letters:                                             # fit.py:268-276, param.py:107-126
+            pp = {par: allp[f"{par}_{L}"] for par in self.pars}
+            try:
+                validate_default(to_default(self.parameterisation, pp))
+            except InvalidParams:
+                return "astro", None
+        for inst in self.unique:                                           # fit.py:282-293
+            if allp[f"jit_{inst}"] < 0:
+                return "astro", None
+        try:
+            lp = self.log_prior(self.params_for_prior(free))               # fit.py:1057-1058
+        except InvalidParams:
+            return "astro", None
+        if not np.isfinite(lp):
+            return "prior", None
+        return "ok", float(lp)
+
+    # ------------------------------------------------------------------ GP conditioning (row f-4; parity unpinned)
+    def _gp_system(self, params: dict, hyper: dict):
+        A, le, lp_, Pg = (hyper[k] for k in ("gp_amp", "gp_lambda_e", "gp_lambda_p", "gp_period"))
+        gamma = 1 / (2 * lp_ ** 2)
+
+        def kern(t1, t2):
+            tau = t1[:, None] - t2[None, :]
+            return A ** 2 * np.exp(-gamma * np.sin(np.pi * np.abs(tau) / Pg) ** 2) * np.exp(-0.5 * (tau / le) ** 2)
+
+        jit = np.array([params[f"jit_{i}"] for i in self.unique])[self.inst_idx]
+        C = kern(self.time, self.time) + np.diag(self.velerr_sq + jit ** 2)         # fit.py:6399, 7531
+        rv = np.zeros(len(self.time))
+        for L in self.letters:
+            rv += planet_rv(self.parameterisation, {par: params[f"{par}_{L}"] for par in self.pars}, self.time)
+        rv += trend_rv(params["gd"], params["gdd"], self.time, self.t0)
+        gam = np.array([params[f"g_{i}"] for i in self.unique])[self.inst_idx]
+        resid = (self.vel - gam) - rv                                                # fit.py:7543-7550
+        return kern, C, resid
+
+    def gp_predict(self, combined: dict, times: np.ndarray) -> tuple[np.ndarray, float]:
+        """fit.py:7494-7554 (`gp.condition(y=residuals, X_test=times)` mean, zero GP mean function) and
+        fit.py:5386-5429 (chi2 = alpha.alpha): mu* = K(t*, t) C^-1 r, restated with a dense Cholesky."""
+        from scipy.linalg import cho_solve, solve_triangular
+        allp = self.fixed | {k: combined[k] for k in self.free_names}
+        allh = self.fixed_hyper | {k: combined[k] for k in self.free_hyper}
+        kern, C, resid = self._gp_system(allp, allh)
+        Lc = np.linalg.cholesky(C)
+        alpha = solve_triangular(Lc, resid, lower=True)
+        beta = cho_solve((Lc, True), resid)
+        return kern(np.asarray(times, dtype=np.float64), self.time) @ beta, float(alpha @ alpha)

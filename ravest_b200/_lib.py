@@ -20,7 +20,7 @@ CSRC = os.path.join(_HERE, "csrc")
 # RVLP_LIB lets tools/kernel_sweep.py time alternative builds of the same sources; it is not a fallback
 LIB_PATH = os.environ.get("RVLP_LIB") or os.path.join(CSRC, "libravest_b200.so")
 SOURCES = ["rvlp_capi.cu"]
-HEADERS = ["rvlp_math.cuh", "rvlp_kernels.cuh", "rvlp_gp.cuh", os.path.join("..", "..", "include", "ravest_b200.h")]
+HEADERS = ["rvlp_math.cuh", "rvlp_kernels.cuh", "rvlp_gp.cuh", "rvlp_bands.cuh", os.path.join("..", "..", "include", "ravest_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -28,8 +28,13 @@ EXPORTS = [
     "rvlp_abi_version", "rvlp_last_error", "rvlp_ctx_create", "rvlp_ctx_destroy", "rvlp_logprob_batch",
     "rvlp_logprob_batch_host", "rvlp_logprob_parts_batch", "rvlp_rv_batch", "rvlp_gp_logprob_batch",
     "rvlp_kepler_rv", "rvlp_planet_rv", "rvlp_trend_rv", "rvlp_convert_to_default", "rvlp_prior_eval",
-    "rvlp_measure_fp64_peak", "rvlp_launch_count",
+    "rvlp_measure_fp64_peak", "rvlp_launch_count", "rvlp_rv_batch_frozen", "rvlp_walker_check_batch",
+    "rvlp_gp_predict_batch", "rvlp_percentile_workspace_bytes", "rvlp_percentile_columns",
 ]
+MAX_FROZEN = 16
+MAX_PERCENTILES = 8
+# rvlp_walker_check_batch status bits (include/ravest_b200.h)
+WALKER_NONFINITE, WALKER_PLANET, WALKER_JITTER, WALKER_PRIOR, WALKER_HYPER, WALKER_HYPERPRIOR = 1, 2, 4, 8, 16, 32
 
 
 class RvlpError(RuntimeError):
@@ -85,8 +90,15 @@ def load() -> C.CDLL:
     lib.rvlp_convert_to_default.argtypes = [i32, vp, i64, vp, vp, C.c_int, vp]
     lib.rvlp_prior_eval.argtypes = [C.POINTER(PriorPOD), vp, i64, vp, C.c_int, vp]
     lib.rvlp_measure_fp64_peak.argtypes = [C.c_int, C.c_int, C.POINTER(dbl), C.POINTER(dbl)]
+    lib.rvlp_rv_batch_frozen.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp, vp, vp]
+    lib.rvlp_walker_check_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.rvlp_gp_predict_batch.argtypes = [vp, vp, i64, vp, i64, vp, vp, vp]
+    lib.rvlp_percentile_workspace_bytes.argtypes = [i64, i32]
+    lib.rvlp_percentile_workspace_bytes.restype = i64
+    lib.rvlp_percentile_columns.argtypes = [vp, i64, i64, vp, i32, vp, vp, i64, C.c_int, vp]
     for name in EXPORTS:
-        if name not in ("rvlp_last_error", "rvlp_launch_count", "rvlp_ctx_destroy"):
+        if name not in ("rvlp_last_error", "rvlp_launch_count", "rvlp_ctx_destroy",
+                        "rvlp_percentile_workspace_bytes"):
             getattr(lib, name).restype = C.c_int
     lib.rvlp_launch_count.restype = i64
     if lib.rvlp_abi_version() != 1:
@@ -144,6 +156,31 @@ def prior_eval(prior, values):
     check(lib.rvlp_prior_eval(C.byref(pod), x.data_ptr(), x.numel(), out.data_ptr(), x.device.index,
                               stream_ptr(x.device.index)))
     return out if is_tensor else out.cpu().numpy()
+
+
+def percentile_columns(matrix, q, out=None):
+    """`np.percentile(matrix, q, axis=0)` on the device (fit.py:2239-2240, 2493-2495): matrix [S, T] CUDA
+    fp64 tensor (or array-like, copied to the device) -> [len(q), T]; tensor in, tensor out."""
+    torch = _torch()
+    lib = load()
+    is_tensor = isinstance(matrix, torch.Tensor)
+    A = as_cuda_f64(matrix)
+    if A.dim() != 2:
+        raise ValueError(f"matrix must be 2-D (samples x times), got shape {tuple(A.shape)}")
+    scalar_q = np.ndim(q) == 0
+    qh = np.ascontiguousarray(np.atleast_1d(q), dtype=np.float64)
+    if qh.ndim != 1 or not 1 <= len(qh) <= MAX_PERCENTILES:
+        raise ValueError(f"q must hold 1..{MAX_PERCENTILES} percentiles")
+    S, T = A.shape
+    dev = A.device.index
+    if out is None:
+        out = torch.empty((len(qh), T), dtype=torch.float64, device=A.device)
+    nbytes = lib.rvlp_percentile_workspace_bytes(T, len(qh))
+    ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=A.device)
+    check(lib.rvlp_percentile_columns(A.data_ptr(), S, T, qh.ctypes.data, len(qh), out.data_ptr(), ws.data_ptr(),
+                                      ws.numel(), dev, stream_ptr(dev)))
+    res = out[0] if scalar_q else out
+    return res if is_tensor else res.cpu().numpy()
 
 
 def measure_fp64_peak(device: int = 0, iters: int = 4096) -> tuple[float, float]:
@@ -225,12 +262,44 @@ class Context:
         check(self._lib.rvlp_logprob_batch_host(self._h, th.ctypes.data, th.shape[0], out_np.ctypes.data))
         return out_np
 
-    def rv_matrix(self, theta, times, component: int, out=None):
+    def rv_matrix(self, theta, times, component: int, out=None, frozen: dict | None = None):
+        """[S, T] RV of `component` (planet number, RV_TREND = -1, RV_TOTAL = -2) for every row of theta.
+        `frozen` maps model-parameter NAMES to values that override every row (fit.py:2726-2751)."""
         torch = _torch()
         th = self._theta(theta)
         tt = as_cuda_f64(times, self.device).reshape(-1)
         if out is None:
             out = torch.empty((th.shape[0], tt.numel()), dtype=torch.float64, device=th.device)
-        check(self._lib.rvlp_rv_batch(self._h, th.data_ptr(), th.shape[0], tt.data_ptr(), tt.numel(),
-                                      int(component), out.data_ptr(), stream_ptr(self.device)))
+        if frozen:
+            idx = np.array([self.desc.model_names.index(k) for k in frozen], dtype=np.int32)
+            val = np.array([float(v) for v in frozen.values()], dtype=np.float64)
+            check(self._lib.rvlp_rv_batch_frozen(self._h, th.data_ptr(), th.shape[0], tt.data_ptr(), tt.numel(),
+                                                 int(component), len(idx), idx.ctypes.data, val.ctypes.data,
+                                                 out.data_ptr(), stream_ptr(self.device)))
+        else:
+            check(self._lib.rvlp_rv_batch(self._h, th.data_ptr(), th.shape[0], tt.data_ptr(), tt.numel(),
+                                          int(component), out.data_ptr(), stream_ptr(self.device)))
         return out
+
+    def walker_check(self, theta):
+        """(status int32[S], log_prior[S], log_hyperprior[S]) - rvlp_walker_check_batch; status 0 = usable row."""
+        torch = _torch()
+        th = self._theta(theta)
+        st = torch.empty(th.shape[0], dtype=torch.int32, device=th.device)
+        lp = torch.empty(th.shape[0], dtype=torch.float64, device=th.device)
+        lhp = torch.empty_like(lp)
+        check(self._lib.rvlp_walker_check_batch(self._h, th.data_ptr(), th.shape[0], st.data_ptr(), lp.data_ptr(),
+                                                lhp.data_ptr(), stream_ptr(self.device)))
+        return st, lp, lhp
+
+    def gp_predict(self, theta, times, want_chi2: bool = False):
+        """GP conditional mean [S, T] at `times` (and alpha.alpha [S]) for every row - rvlp_gp_predict_batch."""
+        torch = _torch()
+        th = self._theta(theta)
+        tt = as_cuda_f64(times, self.device).reshape(-1)
+        mean = torch.empty((th.shape[0], tt.numel()), dtype=torch.float64, device=th.device)
+        chi2 = torch.empty(th.shape[0], dtype=torch.float64, device=th.device) if want_chi2 else None
+        check(self._lib.rvlp_gp_predict_batch(self._h, th.data_ptr(), th.shape[0], tt.data_ptr(), tt.numel(),
+                                              mean.data_ptr(), chi2.data_ptr() if want_chi2 else None,
+                                              stream_ptr(self.device)))
+        return (mean, chi2) if want_chi2 else mean

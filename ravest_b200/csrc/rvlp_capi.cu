@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "rvlp_bands.cuh"
 #include "rvlp_gp.cuh"
 #include "rvlp_kernels.cuh"
 
@@ -94,7 +95,7 @@ struct rvlp_ctx {
   void* d_src_const = nullptr;
   void* d_priors = nullptr;
   void* d_epochs = nullptr;
-  int smem_main = 0, smem_gp = 0, smem_gp_tiled = 0, smem_gp_blocked = 0, gp_tile = 0;
+  int smem_main = 0, smem_gp = 0, smem_gp_tiled = 0, smem_gp_blocked = 0, gp_tile = 0, smem_gp_predict = 0;
   int max_smem = 0;
   // host-buffer path
   double* h_theta = nullptr;
@@ -198,6 +199,7 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
   }
   CTX_TRY(cudaFuncSetAttribute(logprob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   CTX_TRY(cudaFuncSetAttribute(rv_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+  CTX_TRY(cudaFuncSetAttribute(walker_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   if (P.n_hyper) {
     c->smem_gp = gp_smem(P, L).total;
     if (c->smem_gp > c->max_smem) {
@@ -207,6 +209,8 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
       return rc;
     }
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CTX_TRY(cudaFuncSetAttribute(gp_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    c->smem_gp_predict = gp_predict_smem(P, L).total;
     c->gp_tile = gp_tile_for(P.n_epochs);
     c->smem_gp_tiled = gp_tiled_smem(P, L).total;
     c->smem_gp_blocked = c->gp_tile ? gp_blocked_smem(P, L, c->gp_tile).total : 0;
@@ -327,7 +331,24 @@ int rvlp_logprob_batch_host(rvlp_ctx* c, const double* theta_host, int64_t S, do
 
 int rvlp_rv_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const double* times_dev, int64_t T,
                   int32_t component, double* out_dev, void* stream) {
+  return rvlp_rv_batch_frozen(c, theta_dev, S, times_dev, T, component, 0, nullptr, nullptr, out_dev, stream);
+}
+
+int rvlp_rv_batch_frozen(rvlp_ctx* c, const double* theta_dev, int64_t S, const double* times_dev, int64_t T,
+                         int32_t component, int32_t n_frozen, const int32_t* frozen_index,
+                         const double* frozen_value, double* out_dev, void* stream) {
   if (!c || S < 0 || T < 0) return fail(RVLP_EINVAL, "bad arguments");
+  if (n_frozen < 0 || n_frozen > RVLP_MAX_FROZEN) return fail(RVLP_EINVAL, "n_frozen %d not in [0, %d]", n_frozen, RVLP_MAX_FROZEN);
+  if (n_frozen && (!frozen_index || !frozen_value)) return fail(RVLP_EINVAL, "null frozen arrays");
+  FrozenParams frozen{};
+  frozen.n = n_frozen;
+  for (int i = 0; i < n_frozen; ++i) {
+    // fit.py:2631-2638: only planet parameters of the active parameterisation can be frozen
+    if (frozen_index[i] < 0 || frozen_index[i] >= 5 * c->P.n_planets)
+      return fail(RVLP_EINVAL, "frozen_index[%d] = %d is not a planet parameter", i, frozen_index[i]);
+    frozen.idx[i] = frozen_index[i];
+    frozen.val[i] = frozen_value[i];
+  }
   if (component < RVLP_RV_TOTAL || component >= c->P.n_planets) return fail(RVLP_EINVAL, "bad component %d", component);
   if (S == 0 || T == 0) return RVLP_OK;
   if (!theta_dev || !times_dev || !out_dev) return fail(RVLP_EINVAL, "null pointer");
@@ -337,7 +358,23 @@ int rvlp_rv_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const double*
   int rc = grid_for(c->device, (const void*)rv_matrix_kernel, c->smem_main, want, &grid);
   if (rc) return rc;
   rv_matrix_kernel<<<grid, kThreads, c->smem_main, (cudaStream_t)stream>>>(c->P, theta_dev, S, times_dev, T,
-                                                                           component, out_dev);
+                                                                           component, out_dev, frozen);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return RVLP_OK;
+}
+
+int rvlp_walker_check_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, int32_t* status_dev,
+                            double* lp_dev, double* lhp_dev, void* stream) {
+  if (!c || S < 0 || (S > 0 && (!theta_dev || !status_dev))) return fail(RVLP_EINVAL, "bad arguments");
+  if (S == 0) return RVLP_OK;
+  DeviceGuard guard(c->device);
+  int grid = 0;
+  const int64_t want = ((S + kG - 1) / kG + kWarps - 1) / kWarps;
+  int rc = grid_for(c->device, (const void*)walker_check_kernel, c->smem_main, want, &grid);
+  if (rc) return rc;
+  walker_check_kernel<<<grid, kThreads, c->smem_main, (cudaStream_t)stream>>>(c->P, theta_dev, S, status_dev,
+                                                                              lp_dev, lhp_dev);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return RVLP_OK;
@@ -382,6 +419,101 @@ int rvlp_gp_logprob_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
   }
 #undef RVLP_GP_TILED
   ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return RVLP_OK;
+}
+
+int rvlp_gp_predict_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const double* times_dev, int64_t T,
+                          double* mean_dev, double* chi2_dev, void* stream) {
+  if (!c || S < 0 || T < 0 || (S > 0 && !theta_dev)) return fail(RVLP_EINVAL, "bad arguments");
+  if (c->P.n_hyper != 4) return fail(RVLP_EINVAL, "context was not created with GP hyperparameters");
+  if (T > 0 && (!times_dev || !mean_dev)) return fail(RVLP_EINVAL, "null times / mean pointer");
+  if (S == 0 || (T == 0 && !chi2_dev)) return RVLP_OK;
+  if (c->smem_gp_predict > c->max_smem)
+    return fail(RVLP_EUNSUPPORTED, "GP conditioning needs %d B of shared memory per CTA (> %d): too many epochs",
+                c->smem_gp_predict, c->max_smem);
+  DeviceGuard guard(c->device);
+  int grid = 0;
+  int rc = grid_for(c->device, (const void*)gp_predict_kernel, c->smem_gp_predict, S, &grid);
+  if (rc) return rc;
+  gp_predict_kernel<<<grid, kThreads, c->smem_gp_predict, (cudaStream_t)stream>>>(c->P, theta_dev, S, times_dev, T,
+                                                                                  mean_dev, chi2_dev);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return RVLP_OK;
+}
+
+int64_t rvlp_percentile_workspace_bytes(int64_t n_cols, int32_t n_q) {
+  if (n_cols < 0 || n_q < 1 || n_q > RVLP_MAX_PERCENTILES) return -1;
+  return (int64_t)band_ws_bytes(n_cols, 2 * n_q);
+}
+
+int rvlp_percentile_columns(const double* A_dev, int64_t S, int64_t T, const double* q_percent, int32_t n_q,
+                            double* out_dev, void* ws_dev, int64_t ws_bytes, int device, void* stream) {
+  if (S < 0 || T < 0 || n_q < 1 || n_q > RVLP_MAX_PERCENTILES || !q_percent)
+    return fail(RVLP_EINVAL, "bad arguments (n_q must be 1..%d)", RVLP_MAX_PERCENTILES);
+  if (S >= ((int64_t)1 << 31)) return fail(RVLP_EUNSUPPORTED, "more than 2^31 - 1 rows");
+  for (int i = 0; i < n_q; ++i)
+    if (!(q_percent[i] >= 0.0 && q_percent[i] <= 100.0))
+      return fail(RVLP_EINVAL, "Percentiles must be in the range [0, 100]");   // numpy's ValueError
+  if (T == 0) return RVLP_OK;
+  if (!out_dev) return fail(RVLP_EINVAL, "null output");
+  DeviceGuard guard(device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (S == 0) {                                   // numpy: NaN (with a RuntimeWarning)
+    std::vector<double> nanv((size_t)n_q * T, NAN);
+    CUDA_TRY(cudaMemcpyAsync(out_dev, nanv.data(), nanv.size() * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return RVLP_OK;
+  }
+  if (!A_dev || !ws_dev) return fail(RVLP_EINVAL, "null matrix / workspace");
+  const int R = 2 * n_q;
+  if (ws_bytes < (int64_t)band_ws_bytes(T, R) || ((uintptr_t)ws_dev & 255))
+    return fail(RVLP_EINVAL, "workspace too small (%lld < %lld bytes) or not 256-byte aligned", (long long)ws_bytes,
+                (long long)band_ws_bytes(T, R));
+  // numpy/lib/_function_base_impl.py: q = true_divide(q, 100); _compute_virtual_index(n, q, 1, 1) =
+  // n*q + (1 + q*(1 - 1 - 1)) - 1; _get_indexes (floor, +1, clamp at the ends); _get_gamma = virtual - previous.
+  BandTargets tg{};
+  tg.n_q = n_q;
+  for (int i = 0; i < n_q; ++i) {
+    volatile double q = q_percent[i] / 100.0;
+    volatile double nq = (double)S * q;
+    volatile double inner = q * -1.0;
+    inner = 1.0 + inner;
+    volatile double virt = nq + inner;
+    virt = virt - 1.0;
+    double prev = floor(virt), next = prev + 1.0;
+    if (virt >= (double)(S - 1)) prev = next = -1.0;
+    if (virt < 0) prev = next = 0.0;
+    volatile double gam = virt - prev;            // with prev = -1 numpy's gamma is virt + 1: harmless, a == b
+    const int64_t kp = prev < 0 ? S - 1 : (int64_t)prev, kn = next < 0 ? S - 1 : (int64_t)next;
+    tg.k[2 * i] = (uint32_t)kp;
+    tg.k[2 * i + 1] = (uint32_t)kn;
+    tg.gamma[i] = gam;
+  }
+  const BandWorkspace W = band_ws_carve(ws_dev, T, R);
+  CUDA_TRY(cudaMemsetAsync(W.hist, 0, (size_t)T * R * 256 * 4, st));   // level 0 accumulates into buffer 0
+  CUDA_TRY(cudaMemsetAsync(W.nan, 0, (size_t)T * 4, st));
+  const int smem = band_smem_bytes(R);
+  static bool attr_done = false;
+  if (!attr_done) {
+    CUDA_TRY(cudaFuncSetAttribute(band_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(kMaxTargets)));
+    attr_done = true;
+  }
+  int sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  const int64_t ncb = (T + kColBlock - 1) / kColBlock;
+  // row split: ~4 CTAs per SM in total, but at least 2048 rows per CTA so that the per-CTA scan / merge stays small
+  int64_t split = (4 * (int64_t)sms + ncb - 1) / ncb;
+  const int64_t max_split = (S + 2047) / 2048;
+  if (split > max_split) split = max_split;
+  if (split < 1) split = 1;
+  if (split > 65535) split = 65535;
+  for (int level = 0; level <= kLevels; ++level) {
+    const dim3 grid((unsigned)ncb, level == kLevels ? 1u : (unsigned)split);
+    band_level_kernel<<<grid, kBandThreads, smem, st>>>(A_dev, S, T, level, tg, W, out_dev);
+    ++g_launches;
+  }
   CUDA_TRY(cudaGetLastError());
   return RVLP_OK;
 }

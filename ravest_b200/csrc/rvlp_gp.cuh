@@ -558,4 +558,138 @@ gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_
   }
 }
 
+// ------------------------------------------------------------------ K7: GP conditioning (row f-4)
+// Replaces the per-sample loop of GPFitter's posterior predictions (fit.py:6383-6414, 7494-7554:
+// `gp.condition(y = vel - gamma - planets - trend, X_test = times).gp.mean`) and GPFitter._compute_gp_chi2
+// (fit.py:5386-5429, alpha.alpha with alpha = L^-1 r).  tinygp's conditional mean with its default zero mean
+// function is  mu*(t*) = k(t*, t)^T C^-1 r  (restated; "parity unpinned" like K3).
+// One CTA per sample: the smem factorisation of gp_logprob_kernel (row N = residual -> alpha), then a
+// column-oriented back substitution beta = L^-T alpha that walks L's rows (contiguous in the packed
+// triangle), then mu*_i = sum_j k(t*_i - t_j) beta_j with one thread per test time.
+struct GpPredictSmem { int off_tri, off_beta, off_red, total; };
+__host__ __device__ inline GpPredictSmem gp_predict_smem(const DevProblem& P, const SmemLayout& L) {
+  GpPredictSmem G;
+  int o = (L.total + 15) & ~15;
+  G.off_tri = o; o += gp_tri_doubles(P.n_epochs) * 8;
+  G.off_beta = o; o += ((P.n_epochs + 1) & ~1) * 8;
+  G.off_red = o; o += 64 * 8;
+  G.total = o;
+  return G;
+}
+
+__global__ void __launch_bounds__(kThreads)
+gp_predict_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, const double* __restrict__ times,
+                  int64_t T_n, double* __restrict__ mean_out, double* __restrict__ chi2_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout L = smem_layout(P);
+  const GpPredictSmem G = gp_predict_smem(P, L);
+  stage_problem(P, L, smem);
+  const Tables T = tables_of(L, smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
+  double* scratch = reinterpret_cast<double*>(smem + L.off_scratch);
+  double* Cm = reinterpret_cast<double*>(smem + G.off_tri);
+  double* beta = reinterpret_cast<double*>(smem + G.off_beta);
+  double* red = reinterpret_cast<double*>(smem + G.off_red);
+  const int N = P.n_epochs;
+  const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+
+  for (int64_t s = blockIdx.x; s < S; s += gridDim.x) {
+    if (warp == 0) sample_prologue(P, T, theta, s, s + 1, scratch, rec, lane, false, 1);
+    __syncthreads();
+    const double* sr = scratch;
+    const int flags = __double2loint(sr[1]);
+    // The reference raises for such a sample (Planet.__init__ ValueError / build_kernel ValueError); rows are NaN.
+    int bad = (flags & (F_PLANET | F_HYPER)) ? 1 : 0;
+    const double* row = theta + s * P.ndim;
+    const double A = model_param(T, row, P.n_model + 0), le = model_param(T, row, P.n_model + 1);
+    const double lpp = model_param(T, row, P.n_model + 2), Pg = model_param(T, row, P.n_model + 3);
+    const double gamma = 1.0 / (2.0 * (lpp * lpp));          // gp.py:152
+    const double A2 = A * A, inv_le = 1.0 / le, inv_Pg = 1.0 / Pg;
+    if (!bad) {
+      for (int i = tid; i < N; i += kThreads) {              // fit.py:6375-6380, 7536-7550
+        double tt[1] = {T.t[i]}, rv[1];
+        model_rv<1>(P, sr, tt, rv, -1, true);
+        Cm[tri(N, i)] = (T.v[i] - sr[kHdr + T.inst[i]]) - rv[0];
+      }
+      const int npairs = N * (N + 1) / 2;
+      for (int p = tid; p < npairs; p += kThreads) {         // gp.py:145-156; diag fit.py:6399, 7531
+        int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+        while (tri(i + 1, 0) <= p) ++i;
+        while (tri(i, 0) > p) --i;
+        const int j = p - tri(i, 0);
+        const double tau = T.t[i] - T.t[j];
+        const double sn = sinpi(fabs(tau) * inv_Pg);
+        const double q = tau * inv_le;
+        double c = A2 * exp(-gamma * (sn * sn) - 0.5 * (q * q));
+        if (i == j) c += T.e2[i] + sr[kHdr + P.n_inst + T.inst[i]];
+        Cm[p] = c;
+      }
+    }
+    if (__syncthreads_or(bad)) {
+      for (int64_t i = tid; i < T_n; i += kThreads) mean_out[s * T_n + i] = qnan;
+      if (tid == 0 && chi2_out) chi2_out[s] = qnan;
+      __syncthreads();
+      continue;
+    }
+    for (int j = 0; j < N; ++j) {                            // right-looking Cholesky, rows 0..N
+      const double djj = sqrt(Cm[tri(j, j)]);
+      const double inv = 1.0 / djj;
+      __syncthreads();
+      for (int i = j + 1 + tid; i <= N; i += kThreads) Cm[tri(i, j)] *= inv;
+      if (tid == 0) Cm[tri(j, j)] = djj;
+      __syncthreads();
+      const int m = N - j;
+      const int cnt = m * (m + 1) / 2;
+      for (int p = tid; p < cnt; p += kThreads) {
+        int a = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+        while ((a + 1) * (a + 2) / 2 <= p) ++a;
+        while (a * (a + 1) / 2 > p) --a;
+        const int b = p - a * (a + 1) / 2;
+        const int i = j + 1 + a, k = j + 1 + b;
+        if (i == N && k == N) continue;
+        Cm[tri(i, k)] = fma(-Cm[tri(i, j)], Cm[tri(k, j)], Cm[tri(i, k)]);
+      }
+      __syncthreads();
+    }
+    // chi^2 = alpha . alpha (fit.py:5428-5429), fixed-order reduction
+    double q = 0.0;
+    for (int i = tid; i < N; i += kThreads) {
+      const double a = Cm[tri(N, i)];
+      beta[i] = a;
+      q = fma(a, a, q);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) red[warp] = q;
+    __syncthreads();
+    if (tid == 0 && chi2_out) {
+      double quad = 0.0;
+      for (int w = 0; w < kWarps; ++w) quad += red[w];
+      chi2_out[s] = quad;
+    }
+    // beta = L^-T alpha, last unknown first: beta_j = y_j / L_jj, then y_i -= L_ji beta_j for i < j
+    for (int j = N - 1; j >= 0; --j) {
+      const double bj = beta[j] / Cm[tri(j, j)];
+      __syncthreads();                                       // everyone has read beta[j]
+      if (tid == 0) beta[j] = bj;
+      for (int i = tid; i < j; i += kThreads) beta[i] = fma(-Cm[tri(j, i)], bj, beta[i]);
+      __syncthreads();
+    }
+    // conditional mean at the requested times
+    for (int64_t i = tid; i < T_n; i += kThreads) {
+      const double ts = times[i];
+      double acc = 0.0;
+      for (int j = 0; j < N; ++j) {
+        const double tau = ts - T.t[j];
+        const double sn = sinpi(fabs(tau) * inv_Pg);
+        const double qq = tau * inv_le;
+        acc = fma(A2 * exp(-gamma * (sn * sn) - 0.5 * (qq * qq)), beta[j], acc);
+      }
+      mean_out[s * T_n + i] = acc;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace rvlp

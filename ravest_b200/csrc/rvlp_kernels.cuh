@@ -154,6 +154,22 @@ __device__ __forceinline__ void stage_problem(const DevProblem& P, const SmemLay
   __syncthreads();
 }
 
+// Per-call overrides of model parameters (Fitter._resolve_freeze_params, fit.py:2586-2688: `params.update(
+// resolved_freeze)` for every sample): entry i pins model parameter idx[i] to val[i] for this launch only by
+// patching the CTA's shared-memory copy of the source table.
+struct FrozenParams {
+  int n;
+  int idx[RVLP_MAX_FROZEN];
+  double val[RVLP_MAX_FROZEN];
+};
+__device__ __forceinline__ void apply_frozen(const FrozenParams& F, const SmemLayout& L, unsigned char* smem) {
+  if ((int)threadIdx.x < F.n) {
+    reinterpret_cast<double*>(smem + L.off_srcconst)[F.idx[threadIdx.x]] = F.val[threadIdx.x];
+    reinterpret_cast<int*>(smem + L.off_srccol)[F.idx[threadIdx.x]] = -1;
+  }
+  __syncthreads();
+}
+
 // ------------------------------------------------------------------ per-sample prologue
 struct Tables {
   const double* t;
@@ -507,10 +523,12 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
 // ------------------------------------------------------------------ K2: RV matrix (fit.py:2690-2824)
 __global__ void __launch_bounds__(kThreads, RVLP_MIN_BLOCKS)
 rv_matrix_kernel(DevProblem P, const double* __restrict__ theta, int64_t S,
-                 const double* __restrict__ times, int64_t T_n, int component, double* __restrict__ out) {
+                 const double* __restrict__ times, int64_t T_n, int component, double* __restrict__ out,
+                 FrozenParams frozen) {
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = smem_layout(P);
   stage_problem(P, L, smem);
+  if (frozen.n) apply_frozen(frozen, L, smem);     // kernel-uniform
   const Tables T = tables_of(L, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
@@ -550,6 +568,48 @@ rv_matrix_kernel(DevProblem P, const double* __restrict__ theta, int64_t S,
         for (int j = 0; j < kW; ++j)
           if (idx[j] < T_n) orow[idx[j]] = rv[j];
       }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ K5: walker-position check (row f-3)
+// What Fitter.generate_initial_walker_positions_* and run_mcmc do per candidate row before sampling
+// (fit.py:692-725, 884-902, 1048-1062; GP twin fit.py:4500-4540, 4950-4990): _validate_astrophysical_validity
+// (fit.py:260-293: every parameter finite, each planet converts + validates, jitter >= 0) then a finite
+// log-prior on the converted parameters.  One status word per row instead of one LogPosterior per attempt.
+__global__ void __launch_bounds__(kThreads, RVLP_MIN_BLOCKS)
+walker_check_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, int32_t* __restrict__ status,
+                    double* __restrict__ lp_out, double* __restrict__ lhp_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout L = smem_layout(P);
+  stage_problem(P, L, smem);
+  const Tables T = tables_of(L, smem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
+  double* scratch = reinterpret_cast<double*>(smem + L.off_scratch) + warp * kG * rec;
+  const int64_t n_batches = (S + kG - 1) / kG;
+  const int64_t gw = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
+  for (int64_t b = gw; b < n_batches; b += nw) {
+    const int64_t s0 = b * kG;
+    sample_prologue(P, T, theta, s0, S, scratch, rec, lane, true);
+    if (lane < kG && s0 + lane < S) {
+      const int64_t s = s0 + lane;
+      const double* row = theta + s * P.ndim;
+      const double* sr = scratch + lane * rec;
+      const int flags = __double2loint(sr[1]);
+      int st = 0;
+      for (int i = 0; i < P.n_model + P.n_hyper; ++i)          // fit.py:262-265 (free and fixed values alike)
+        if (!(fabs(model_param(T, row, i)) <= 1.79769313486231570e308)) st |= RVLP_WALKER_NONFINITE;
+      if (flags & F_PLANET) st |= RVLP_WALKER_PLANET;          // fit.py:268-276
+      if (flags & F_JIT) st |= RVLP_WALKER_JITTER;             // fit.py:289-293
+      if (flags & F_HYPER) st |= RVLP_WALKER_HYPER;            // gp.py:82-108
+      const double lp = sr[0], lhp = sr[4];
+      if (!(fabs(lp) <= 1.79769313486231570e308)) st |= RVLP_WALKER_PRIOR;        // fit.py:717-720
+      if (!(fabs(lhp) <= 1.79769313486231570e308)) st |= RVLP_WALKER_HYPERPRIOR;  // fit.py:4534-4537
+      status[s] = st;
+      if (lp_out) lp_out[s] = lp;
+      if (lhp_out) lhp_out[s] = lhp;
     }
     __syncwarp();
   }

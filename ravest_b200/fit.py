@@ -15,6 +15,7 @@ device context and rebuilding it lazily.
 from __future__ import annotations
 
 import logging
+import warnings
 from typing import Callable, Dict
 
 import numpy as np
@@ -112,6 +113,107 @@ class _DeviceBacked:
         return self.ctx.logprob_host(np.asarray(theta, dtype=np.float64))
 
 
+class _SampleMatrices:
+    """Posterior-sample matrices, shared by LogPosterior and GPLogPosterior.
+
+    The reference keeps these on `Fitter` and pulls the rows from its emcee sampler; here they take the
+    `samples[S, ndim]` block (free_params_names order; GP: + free_hyperparams_names) explicitly and return
+    CUDA tensors, so that the S x T matrices stay on the device for the percentile step.
+    """
+
+    RV_TREND, RV_TOTAL = -1, -2
+
+    def _columns(self) -> list[str]:
+        return list(self.free_params_names) + list(getattr(self, "free_hyperparams_names", []))
+
+    def resolve_freeze_params(self, freeze_params, samples=None, planet_letter=None):
+        """fit.py:2586-2688 (_resolve_freeze_params): validate keys, warn, resolve None -> posterior median."""
+        if freeze_params is None:
+            return None
+        valid = {f"{par}_{L}" for par in self.parameterisation.pars for L in self.planet_letters}
+        unknown = set(freeze_params) - valid
+        if unknown:
+            raise ValueError(
+                f"Unknown freeze_params key(s): {sorted(unknown)}. Keys must be planet parameters of the active "
+                f"parameterisation, i.e. one of {sorted(valid)}.")
+        if planet_letter is not None:
+            wrong = [k for k in freeze_params if k.rsplit("_", 1)[-1] != planet_letter]
+            if wrong:
+                warnings.warn(f"freeze_params names parameter(s) for a different planet than '{planet_letter}': "
+                              f"{sorted(wrong)}. Freezing is intended for the target planet's parameters "
+                              f"(typically P and Tc); check the planet letter.", UserWarning, stacklevel=2)
+        fixed_frozen = [k for k in freeze_params if k not in self.free_params_names]
+        if fixed_frozen:
+            warnings.warn(f"freeze_params names parameter(s) that are already fixed, not free: {sorted(fixed_frozen)}. "
+                          f"Freezing only affects parameters that vary across posterior samples, so this has no "
+                          f"de-smearing effect (a None value just resolves to the fixed value). Did you mean a free "
+                          f"parameter, or pass the wrong name?", UserWarning, stacklevel=2)
+        cols = self._columns()
+        resolved = {}
+        for key, value in freeze_params.items():
+            if value is None:
+                if key in cols:
+                    if samples is None:
+                        raise ValueError("samples are needed to resolve a None (posterior median) freeze value")
+                    torch = _lib._torch()
+                    col = samples[:, cols.index(key)]
+                    col = col.detach().cpu().numpy() if isinstance(col, torch.Tensor) else np.asarray(col)
+                    resolved[key] = float(np.median(col))
+                else:
+                    resolved[key] = float(self.fixed_params[key])
+            else:
+                resolved[key] = float(value)
+        return resolved
+
+    def rv_planet_from_samples(self, planet_letter: str, times, samples, freeze_params=None):
+        """Fitter.calculate_rv_planet_from_samples (fit.py:2690-2751) -> CUDA tensor [S, len(times)]."""
+        frozen = self.resolve_freeze_params(freeze_params, samples, planet_letter)
+        return self.ctx.rv_matrix(samples, times, list(self.planet_letters).index(planet_letter), frozen=frozen)
+
+    def rv_trend_from_samples(self, times, samples):
+        """Fitter.calculate_rv_trend_from_samples (fit.py:2753-2789)."""
+        return self.ctx.rv_matrix(samples, times, self.RV_TREND)
+
+    def rv_total_from_samples(self, times, samples):
+        """Fitter.calculate_rv_total_from_samples (fit.py:2791-2824): planets + trend, no gamma."""
+        return self.ctx.rv_matrix(samples, times, self.RV_TOTAL)
+
+    def rv_percentile_bands(self, times, samples, component="total", q=(15.85, 50, 84.15), freeze_params=None):
+        """The matrix + `np.percentile(..., [15.85, 50, 84.15], axis=0)` pair of fit.py:2235-2240, 2468-2495:
+        returns a CUDA tensor [len(q), len(times)]; the S x T matrix never leaves the device."""
+        if component == "total":
+            m = self.rv_total_from_samples(times, samples)
+        elif component == "trend":
+            m = self.rv_trend_from_samples(times, samples)
+        else:
+            m = self.rv_planet_from_samples(component, times, samples, freeze_params)
+        return _lib.percentile_columns(m, q)
+
+    # -- walker initialisation checks (row f-3) ----------------------------------------
+    def check_walker_positions(self, positions):
+        """Per row: (usable, status bits, log_prior) as NumPy arrays - the test each candidate walker goes
+        through in fit.py:692-725, 884-902 (astrophysical validity, then a finite log-prior)."""
+        st, lp, lhp = self.ctx.walker_check(positions)
+        st = st.cpu().numpy()
+        return st == 0, st, lp.cpu().numpy(), lhp.cpu().numpy()
+
+    def validate_initial_positions(self, initial_positions) -> None:
+        """Fitter.run_mcmc's pre-flight loop (fit.py:1048-1062): raise for the first unusable walker."""
+        ok, st, lp, lhp = self.check_walker_positions(initial_positions)
+        if ok.all():
+            return
+        i = int(np.argmin(ok))
+        s = int(st[i])
+        if s & (_lib.WALKER_NONFINITE | _lib.WALKER_PLANET | _lib.WALKER_JITTER | _lib.WALKER_HYPER):
+            why = ("non-finite parameter value" if s & _lib.WALKER_NONFINITE else
+                   "planet parameters fail conversion / validity" if s & _lib.WALKER_PLANET else
+                   "jitter < 0" if s & _lib.WALKER_JITTER else "GP hyperparameter not finite and > 0")
+            raise ValueError(f"Walker {i} has invalid astrophysical parameters: {why}")
+        if s & _lib.WALKER_PRIOR:
+            raise ValueError(f"Walker {i} is outside prior bounds (log_prior = {lp[i]})")
+        raise ValueError(f"Walker {i} is outside hyperprior bounds (log_hyperprior = {lhp[i]})")
+
+
 class LogLikelihood(_DeviceBacked):
     """fit.py:3529-3660 — white-noise Gaussian log-likelihood of ALL parameters."""
 
@@ -146,7 +248,7 @@ class LogLikelihood(_DeviceBacked):
         return float(self.batch(row)[0])
 
 
-class LogPosterior(_DeviceBacked):
+class LogPosterior(_DeviceBacked, _SampleMatrices):
     """fit.py:3228-3526."""
 
     def __init__(self, planet_letters, parameterisation: Parameterisation, priors: dict, fixed_params: dict,
@@ -237,7 +339,7 @@ class GPLogLikelihood(_DeviceBacked):
         return float(self.ctx.logprob_host(row)[0])
 
 
-class GPLogPosterior(_DeviceBacked):
+class GPLogPosterior(_DeviceBacked, _SampleMatrices):
     """fit.py:7596-7939."""
 
     def __init__(self, planet_letters, parameterisation: Parameterisation, gp_kernel: GPKernel, priors: dict,
@@ -273,6 +375,16 @@ class GPLogPosterior(_DeviceBacked):
         names = list(self.free_params_names) + list(self.free_hyperparams_names)
         row = np.array([[float(combined[n]) for n in names]])
         return float(self.ctx.logprob_host(row)[0])
+
+    # -- GP conditioning (row f-4) ------------------------------------------------------
+    def gp_mean_from_samples(self, times, samples):
+        """The per-sample loop of fit.py:6383-6414 / 7494-7554: GP conditional mean at `times`, conditioned on
+        vel - gamma - planets - trend, for every row of samples -> CUDA tensor [S, len(times)]."""
+        return self.ctx.gp_predict(samples, times)
+
+    def chi2_batch(self, samples):
+        """GPFitter._compute_gp_chi2 (fit.py:5386-5429) for every row: r^T C^-1 r."""
+        return self.ctx.gp_predict(samples, np.empty(0), want_chi2=True)[1]
 
     def _negative_log_probability_for_MAP(self, vals) -> float:
         """fit.py:7903-7939."""

@@ -414,6 +414,90 @@ def make_rv_matrix():
     dump("rv_matrix.json", out)
 
 
+def make_sample_matrices():
+    """Rows f-1..f-3: frozen-parameter RV matrices, their percentile bands, walker-position checks.
+    The reference reads its rows from an emcee sampler (absent here): `get_samples_np` / `get_samples_dict`
+    are pointed at the fixture's theta on the Fitter INSTANCE; everything downstream is the reference's code
+    (`_resolve_freeze_params`, `_calculate_rv_planet_from_samples`, `calculate_rv_total_from_samples`,
+    `np.percentile` as called at fit.py:2239-2240, `_validate_astrophysical_validity` + the log-prior test of
+    fit.py:1048-1062)."""
+    import warnings
+    out = {"freeze": [], "walker": []}
+    for par, seed in (("P K secosw sesinw Tc", 41), ("P K e w Tp", 42)):
+        spec, theta = workloads.make_multiplanet(2, 40, 101, seed, parameterisation=par,
+                                                 instruments=("HARPS", "HIRES"), t_span=150.0, invalid_frac=0.0)
+        f = ref_fitter(spec)
+        names = f.free_params_names
+        f.get_samples_np = lambda discard_start=0, discard_end=0, thin=1, flat=False, _t=theta: _t
+        f.get_samples_dict = lambda discard_start=0, discard_end=0, thin=1, _t=theta: {
+            n: _t[:, i] for i, n in enumerate(names)}
+        times = np.linspace(-3, 160, 41)
+        last = par.split()[-1]
+        freeze = {"P_b": None, f"{last}_b": float(np.median(theta[:, names.index(f"{last}_b")]) + 0.01)}
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            resolved = f._resolve_freeze_params(freeze, planet_letter="b")
+        m_frozen = f._calculate_rv_planet_from_samples("b", times, resolved_freeze=resolved)
+        m_plain = f.calculate_rv_planet_from_samples("b", times)
+        m_total = f.calculate_rv_total_from_samples(times)
+        q = [15.85, 50, 84.15]
+        out["freeze"].append({
+            "spec": spec, "free_names": names, "theta": theta, "times": times, "freeze": freeze,
+            "resolved": resolved, "planet_b_frozen": m_frozen, "planet_b": m_plain, "total": m_total, "q": q,
+            "bands_frozen": np.percentile(m_frozen, q, axis=0), "bands_total": np.percentile(m_total, q, axis=0)})
+
+    rng = np.random.default_rng(77)
+    for par, seed, style in (("P K secosw sesinw Tc", 51, None), ("P K e w Tc", 52, None), ("P K e w Tp", 53, None),
+                             ("P K secosw sesinw Tc", 54, "case3")):
+        kw = dict(parameterisation=par, instruments=("HARPS", "HIRES"), t_span=150.0, invalid_frac=0.3)
+        spec, theta = workloads.make_multiplanet(2, 25, 60, seed, **kw)
+        if style == "case3":      # priors on the converted e, w instead of secosw / sesinw (fit.py:3423-3446)
+            pri = dict(spec["priors"])
+            for L in spec["planet_letters"]:
+                pri.pop(f"secosw_{L}"); pri.pop(f"sesinw_{L}")
+                pri[f"e_{L}"] = ("EccentricityUniform", 0.6)
+                pri[f"w_{L}"] = ("Uniform", -np.pi, np.pi)
+            spec = dict(spec, priors=pri)
+        f, lp = ref_logposterior(spec, check_priors=False)
+        names = lp.free_params_names
+        fixed = lp.fixed_params
+        helper = fit.Fitter(list(spec["planet_letters"]), param.Parameterisation(par))
+        helper.unique_instruments = lp.unique_instruments
+
+        def classify(row):
+            d = dict(zip(names, (float(x) for x in row)))
+            try:
+                helper._validate_astrophysical_validity(fixed | d)          # fit.py:1051-1054
+            except ValueError:
+                return "astro", None
+            try:
+                v = lp.log_prior(lp._convert_params_for_prior_evaluation(d))   # fit.py:1057-1058
+            except ValueError:
+                return "astro", None
+            return ("ok", float(v)) if np.isfinite(v) else ("prior", None)
+
+        base = next(r for r in theta if classify(r)[0] == "ok").copy()
+        rows, tags = edge_rows(names, base)
+        for n in names:                                   # non-finite values, fit.py:262-265
+            for bad in (np.nan, np.inf, -np.inf):
+                r = base.copy(); r[names.index(n)] = bad
+                rows.append(r); tags.append(f"{n}={bad}")
+        for n in names:                                   # valid astrophysics, outside the prior: fit.py:1059-1062
+            pr = spec["priors"].get(n)
+            if pr is not None and pr[0] == "Uniform":
+                r = base.copy(); r[names.index(n)] = pr[2] + 0.5 * abs(pr[2]) + 1.0
+                rows.append(r); tags.append(f"{n} above its Uniform prior")
+        if style == "case3":
+            r = base.copy(); r[names.index("secosw_b")] = np.sqrt(0.7); r[names.index("sesinw_b")] = 0.0
+            rows.append(r); tags.append("e_b = 0.7 outside EccentricityUniform(0.6)")
+        theta = np.vstack([theta, np.array(rows)])
+        res = [classify(r) for r in theta]
+        stage, lps = [a for a, _ in res], [b for _, b in res]
+        out["walker"].append({"spec": spec, "free_names": names, "theta": theta, "stage": stage, "log_prior": lps,
+                              "tags": ["random"] * (len(theta) - len(tags)) + tags})
+    dump("sample_matrices.json", out)
+
+
 if __name__ == "__main__":
     import logging
     logging.disable(logging.CRITICAL)
@@ -423,3 +507,4 @@ if __name__ == "__main__":
     make_known_answers()
     make_logprob_cases()
     make_rv_matrix()
+    make_sample_matrices()

@@ -162,6 +162,176 @@ def test_rv_matrix_mode(cuda):
         assert np.isnan(out[0]).all() and np.isfinite(out[1:]).all()
 
 
+# ------------------------------------------------------------------ rows f-1..f-3: sample matrices
+def test_frozen_parameter_rv_matrices(cuda):
+    """fit.py:2586-2751: `params.update(resolved_freeze)` for every sample, against the reference's matrices."""
+    import warnings
+    for c in load_golden("sample_matrices")["freeze"]:
+        post = _post(spec_from_json(c["spec"]))
+        theta, times = np.array(c["theta"]), np.array(c["times"])
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")          # a key of the plotted planet, free: no warning expected
+            resolved = post.resolve_freeze_params(c["freeze"], theta, planet_letter="b")
+        assert resolved == c["resolved"]            # None -> np.median of the column, bit-identical
+        got = post.rv_planet_from_samples("b", times, cuda.as_tensor(theta, device="cuda"), c["freeze"]).cpu().numpy()
+        ref = np.array(c["planet_b_frozen"])
+        K = np.abs(theta[:, c["free_names"].index("K_b")])[:, None]
+        assert np.all(np.abs(got - ref) <= 1e-9 * np.maximum(np.abs(ref), K))
+        plain = post.rv_planet_from_samples("b", times, theta).cpu().numpy()
+        assert np.all(np.abs(plain - np.array(c["planet_b"])) <= 1e-9 * np.maximum(np.abs(plain), K))
+        assert np.abs(plain - got).max() > 1e-3     # freezing did change the matrix
+        # frozen overrides do not leak into later launches of the same context
+        again = post.rv_planet_from_samples("b", times, theta).cpu().numpy()
+        assert np.array_equal(again, plain)
+        with pytest.raises(ValueError, match="Unknown freeze_params"):
+            post.resolve_freeze_params({"gd": 0.0}, theta)
+        with pytest.warns(UserWarning, match="different planet"):
+            post.resolve_freeze_params({"P_c": 3.0}, theta, planet_letter="b")
+        # freezing a planet parameter to an invalid value makes every row NaN (the reference raises)
+        bad = post.rv_planet_from_samples("b", times, theta, {"K_b": -1.0}).cpu().numpy()
+        assert np.isnan(bad).all()
+
+
+def test_percentile_bands_match_numpy_bit_for_bit(cuda):
+    """np.percentile(matrix, [15.85, 50, 84.15], axis=0) (fit.py:2239-2240, 2493-2495): exact order statistics
+    + numpy's _lerp arithmetic -> identical bits.  Ragged shapes, ties, signed zeros, infinities, NaN columns."""
+    from ravest_b200 import _lib
+    rng = np.random.default_rng(11)
+    q = [15.85, 50, 84.15]
+    for c in load_golden("sample_matrices")["freeze"]:
+        for key, bands in (("planet_b_frozen", "bands_frozen"), ("total", "bands_total")):
+            got = _lib.percentile_columns(np.array(c[key]), c["q"])
+            assert np.array_equal(got, np.array(c[bands]))
+    shapes = [(1, 1), (1, 5), (2, 3), (3, 8), (7, 9), (100, 17), (257, 33), (1000, 64), (4099, 7), (20000, 40)]
+    for S, T in shapes:
+        A = rng.normal(3.0, 2.0, size=(S, T))
+        if S >= 7:
+            A[:, 0] = np.round(A[:, 0])                  # heavy ties
+            A[::3, T - 1] = 0.0                          # mixed signed zeros
+            A[1::3, T - 1] = -0.0
+            if T > 2:
+                A[:, 1] = 5.0                            # constant column
+                A[0, 2] = np.inf                         # infinities at the ends
+                A[1, 2] = -np.inf
+        got = _lib.percentile_columns(A, q)
+        ref = np.percentile(A, q, axis=0)
+        assert got.shape == ref.shape
+        assert np.array_equal(got, ref), (S, T, np.abs(got - ref).max())
+    # every percentile numpy special-cases: 0, 100 (virtual index at the ends), exact integers, many at once
+    A = rng.standard_normal((501, 12)) * 1e-3 + 1e3      # narrow spread: the top key digits all agree
+    qq = [0, 100, 50, 20, 99.9, 0.1, 33.3, 75]
+    assert np.array_equal(_lib.percentile_columns(A, qq), np.percentile(A, qq, axis=0))
+    assert np.array_equal(_lib.percentile_columns(A, 50.0), np.percentile(A, 50.0, axis=0))
+    # wide dynamic range + sign changes
+    A = rng.standard_normal((3001, 10)) * 10.0 ** rng.integers(-300, 300, size=(3001, 10))
+    assert np.array_equal(_lib.percentile_columns(A, q), np.percentile(A, q, axis=0))
+    # a NaN anywhere in a column makes that column NaN (numpy sorts NaN last and checks the last element)
+    A = rng.standard_normal((300, 6))
+    A[17, 2] = np.nan
+    A[299, 4] = -np.nan
+    got, ref = _lib.percentile_columns(A, q), np.percentile(A, q, axis=0)
+    assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.isnan(got[:, 2]).all() and np.isnan(got[:, 4]).all()
+    assert np.array_equal(got[:, [0, 1, 3, 5]], ref[:, [0, 1, 3, 5]])
+    with pytest.raises(ValueError, match="range"):
+        _lib.percentile_columns(A, [101.0])
+    # tensor in -> tensor out, and the fused matrix + bands entry of the host mirror
+    t = cuda.as_tensor(A, device="cuda")
+    assert np.array_equal(_lib.percentile_columns(t, q).cpu().numpy(), got)
+
+
+def test_percentile_bands_full_size(cuda):
+    """1e5 samples x 1000 times (BASELINE config 2's posterior size): properties that need no CPU sort of
+    the full matrix - the bands of each column bracket exactly the right number of samples - plus numpy on
+    a column subset."""
+    from ravest_b200 import _lib, workloads
+    spec, theta = workloads.make_c2(100_000)
+    post = _post(spec)
+    times = np.linspace(spec["time"].min(), spec["time"].max(), 1000)
+    good = post.check_walker_positions(theta)[0]
+    th = cuda.as_tensor(theta[good], device="cuda")
+    m = post.rv_total_from_samples(times, th)
+    q = [15.85, 50, 84.15]
+    bands = _lib.percentile_columns(m, q)
+    S = m.shape[0]
+    below = (m <= bands[1][None, :]).sum(0).cpu().numpy()
+    assert np.all(below >= (S + 1) // 2) and np.all((m < bands[1][None, :]).sum(0).cpu().numpy() <= S // 2)
+    cols = [0, 1, 7, 500, 993, 999]
+    ref = np.percentile(m[:, cols].cpu().numpy(), q, axis=0)
+    assert np.array_equal(bands[:, cols].cpu().numpy(), ref)
+    assert np.array_equal(post.rv_percentile_bands(times, th).cpu().numpy(), bands.cpu().numpy())
+
+
+def test_walker_position_checks(cuda):
+    """fit.py:692-725, 884-902, 1048-1062: the reference's verdict for every candidate row."""
+    from ravest_b200 import _lib
+    from oracle import oracle_py
+    for c in load_golden("sample_matrices")["walker"]:
+        spec = spec_from_json(c["spec"])
+        post = _post(spec)
+        theta = np.array(c["theta"], dtype=float)
+        ok, st, lp, _ = post.check_walker_positions(theta)
+        astro = (st & (_lib.WALKER_NONFINITE | _lib.WALKER_PLANET | _lib.WALKER_JITTER)) != 0
+        for i, (stage, tag) in enumerate(zip(c["stage"], c["tags"])):
+            got = "astro" if astro[i] else ("prior" if st[i] & _lib.WALKER_PRIOR else "ok")
+            assert got == stage, (tag, int(st[i]))
+        isok = np.array([s == "ok" for s in c["stage"]])
+        assert np.array_equal(ok, isok)
+        ref_lp = np.array([v for v in c["log_prior"] if v is not None])
+        assert np.all(np.abs(lp[isok] - ref_lp) <= 1e-12 * np.maximum(1.0, np.abs(ref_lp)))
+        # run_mcmc's pre-flight (fit.py:1048-1062)
+        post.validate_initial_positions(theta[isok])
+        first_bad = int(np.argmin(isok))
+        with pytest.raises(ValueError, match=f"Walker {first_bad} "):
+            post.validate_initial_positions(theta)
+    # a larger seeded block against the oracle restatement, ragged size
+    from ravest_b200 import workloads
+    spec, theta = workloads.make_multiplanet(3, 50, 1003, seed=8, instruments=("A", "B"), invalid_frac=0.4)
+    pr = oracle_py.Problem(spec)
+    ok = _post(spec).check_walker_positions(theta)[0]
+    assert np.array_equal(ok, np.array([pr.walker_stage(r)[0] == "ok" for r in theta]))
+    assert 0.2 < ok.mean() < 0.9
+
+
+def test_gp_conditioning_against_restatement(cuda):
+    """Row f-4 (fit.py:6383-6414, 7494-7554, 5386-5429).  Parity unpinned against tinygp (absent): held to the
+    numpy restatement, tolerance scaled by the condition of the solve."""
+    from oracle import oracle_py
+    from ravest_b200 import workloads
+    for n_pl, N, T in ((1, 120, 333), (2, 57, 64), (1, 3, 5)):
+        spec, theta = workloads.make_c5(n_samples=40, n_planets=n_pl, n_epochs=N, seed=700 + N)
+        post = _post(spec)
+        pr = oracle_py.Problem(spec)
+        names = pr.free_names + pr.free_hyper
+        times = np.linspace(spec["time"].min() - 5.0, spec["time"].max() + 5.0, T)
+        mean, chi2 = post.ctx.gp_predict(theta, times, want_chi2=True)
+        mean, chi2 = mean.cpu().numpy(), chi2.cpu().numpy()
+        assert np.array_equal(post.chi2_batch(theta).cpu().numpy(), chi2, equal_nan=True)
+        n_checked = 0
+        for i, row in enumerate(theta):
+            comb = dict(zip(names, map(float, row)))
+            bad_h = min(comb[k] for k in pr.free_hyper) <= 0
+            stage = pr.walker_stage(row[:len(pr.free_names)])[0]
+            planets_bad = False
+            try:
+                for L in pr.letters:
+                    oracle_py.validate_default(oracle_py.to_default(
+                        pr.parameterisation, {q: (pr.fixed | comb)[f"{q}_{L}"] for q in pr.pars}))
+            except oracle_py.InvalidParams:
+                planets_bad = True
+            if bad_h or planets_bad:
+                assert np.isnan(mean[i]).all() and np.isnan(chi2[i])
+                continue
+            mu, c2 = pr.gp_predict(comb, times)
+            scale = max(1.0, np.abs(mu).max())
+            assert np.abs(mean[i] - mu).max() <= 1e-7 * scale, (i, np.abs(mean[i] - mu).max())
+            assert abs(chi2[i] - c2) <= 1e-9 * max(1.0, c2)
+            n_checked += 1
+        assert n_checked >= 20
+    # observation epochs as test times reproduce gp_mean_matrix_obs (fit.py:6407-6410)
+    mo = post.gp_mean_from_samples(spec["time"], theta).cpu().numpy()
+    assert mo.shape == (len(theta), len(spec["time"]))
+
+
 # ------------------------------------------------------------------ oracle on seeded workloads
 @pytest.mark.parametrize("name,S", [("c1", 512), ("c1c", 512), ("c2", 4096), ("c3", 1024), ("c4", 1024)])
 def test_workloads_against_c_oracle(cuda, name, S):

@@ -115,6 +115,53 @@ def test_c_oracle_rv_matrix():
         assert np.array_equal(py.rv_matrix(theta, times, "total"), np.array(c["components"]["total"]))
 
 
+def test_py_oracle_sample_matrices_and_walker_checks_bit_exact():
+    """Rows f-1 / f-3: frozen-parameter RV matrices and the walker-position verdicts of the reference."""
+    g = load_golden("sample_matrices")
+    for c in g["freeze"]:
+        pr = oracle_py.Problem(spec_from_json(c["spec"]))
+        theta, times = np.array(c["theta"]), np.array(c["times"])
+        assert np.array_equal(pr.rv_matrix(theta, times, "b", frozen=c["resolved"]), np.array(c["planet_b_frozen"]))
+        assert np.array_equal(pr.rv_matrix(theta, times, "b"), np.array(c["planet_b"]))
+        assert np.array_equal(pr.rv_matrix(theta, times, "total"), np.array(c["total"]))
+        # the bands ARE numpy's (the reference calls np.percentile, fit.py:2239-2240)
+        assert np.array_equal(np.percentile(np.array(c["total"]), c["q"], axis=0), np.array(c["bands_total"]))
+    n_prior = 0
+    for c in g["walker"]:
+        pr = oracle_py.Problem(spec_from_json(c["spec"]))
+        assert pr.free_names == c["free_names"]
+        for row, stage, lp, tag in zip(np.array(c["theta"], dtype=float), c["stage"], c["log_prior"], c["tags"]):
+            got_stage, got_lp = pr.walker_stage(row)
+            assert got_stage == stage, tag
+            if stage == "ok":
+                assert got_lp == lp, tag
+            n_prior += stage == "prior"
+    assert n_prior >= 10
+
+
+def test_gp_conditioning_restatement_self_consistent():
+    """Row f-4 (parity unpinned, tinygp absent): Cholesky route against a dense solve, and the textbook
+    property that conditioning on noise-free data interpolates it."""
+    from ravest_b200 import workloads
+    spec, theta = workloads.make_c5(n_samples=6, seed=9, n_epochs=30)
+    pr = oracle_py.Problem(spec)
+    names = pr.free_names + pr.free_hyper
+    times = np.linspace(pr.time.min() - 3, pr.time.max() + 3, 17)
+    for row in theta:
+        comb = dict(zip(names, map(float, row)))
+        if pr.walker_stage(row[:len(pr.free_names)])[0] == "astro" or min(comb[k] for k in pr.free_hyper) <= 0:
+            continue
+        mu, chi2 = pr.gp_predict(comb, times)
+        kern, C, resid = pr._gp_system(pr.fixed | {k: comb[k] for k in pr.free_names},
+                                       pr.fixed_hyper | {k: comb[k] for k in pr.free_hyper})
+        assert np.allclose(mu, kern(times, pr.time) @ np.linalg.solve(C, resid), rtol=1e-9, atol=1e-9)
+        assert abs(chi2 - resid @ np.linalg.solve(C, resid)) < 1e-8 * max(1.0, chi2)
+        # at the observed epochs mu = r - D C^-1 r  (K = C - D)
+        mu_obs, _ = pr.gp_predict(comb, pr.time)
+        assert np.allclose(mu_obs, resid - np.diag(C - kern(pr.time, pr.time)) * np.linalg.solve(C, resid),
+                           rtol=1e-9, atol=1e-9)
+
+
 def test_gp_restatement_self_consistent():
     """GP parity is unpinned (tinygp absent): the C and numpy restatements must at least agree with each
     other and with slogdet + solve."""
