@@ -471,17 +471,14 @@ int rvlp_percentile_columns(const double* A_dev, int64_t S, int64_t T, const dou
   if (ws_bytes < (int64_t)band_ws_bytes(T, R) || ((uintptr_t)ws_dev & 255))
     return fail(RVLP_EINVAL, "workspace too small (%lld < %lld bytes) or not 256-byte aligned", (long long)ws_bytes,
                 (long long)band_ws_bytes(T, R));
-  // numpy/lib/_function_base_impl.py: q = true_divide(q, 100); _compute_virtual_index(n, q, 1, 1) =
-  // n*q + (1 + q*(1 - 1 - 1)) - 1; _get_indexes (floor, +1, clamp at the ends); _get_gamma = virtual - previous.
+  // numpy/lib/_function_base_impl.py: q = true_divide(q, 100); method "linear": virtual index = (n - 1) * q
+  // (its comment: preferred to _compute_virtual_index(n, q, 1, 1) for rounding); _get_indexes (floor, +1,
+  // clamped at the ends); _get_gamma = virtual - previous.
   BandTargets tg{};
   tg.n_q = n_q;
   for (int i = 0; i < n_q; ++i) {
     volatile double q = q_percent[i] / 100.0;
-    volatile double nq = (double)S * q;
-    volatile double inner = q * -1.0;
-    inner = 1.0 + inner;
-    volatile double virt = nq + inner;
-    virt = virt - 1.0;
+    volatile double virt = (double)(S - 1) * q;
     double prev = floor(virt), next = prev + 1.0;
     if (virt >= (double)(S - 1)) prev = next = -1.0;
     if (virt < 0) prev = next = 0.0;
