@@ -7,14 +7,17 @@
 // numpy's default ("linear", Hyndman & Fan 7) needs, per column and percentile, the order statistics
 // floor(v) and floor(v)+1 of the virtual index v = q (S-1) and blends them (numpy _lerp).  Exact selection,
 // no sort: an MSB-first radix select on the order-preserving 64-bit image of the doubles, 8 bits per level,
-// all columns and all targets at once.  One launch per level; each launch
-//   1. (level > 0) scans the previous level's histograms and extends every target's key prefix by one digit,
-//   2. streams its slab of rows ONCE (coalesced: a CTA owns kColBlock adjacent columns), counting the next
-//      digit of every element that still matches a live prefix into shared-memory histograms,
-//   3. merges them into the global histogram of the level with integer atomics.
-// After 8 levels the prefixes ARE the order statistics (bit-exact); the last launch blends and stores.
-// Integer counting only: the result does not depend on grid size, row split or arrival order.
-// HBM-bound: 8 passes x S x T x 8 bytes.
+// all columns and all targets at once.  One launch per level; launch L
+//   1. scans level L-1's histograms and extends every target's key prefix to L digits;
+//   2. streams its slab of rows ONCE (coalesced: a CTA owns kColBlock adjacent columns) and counts digit L of
+//      every element that still matches a live prefix into shared-memory histograms (run-length aggregated
+//      per thread: neighbouring samples of a column mostly share their leading digits), OR - as soon as a
+//      column's live elements fit its candidate buffer (typically at L = 3) - copies them out instead;
+//   3. merges the histograms into the level's global histogram with integer atomics.
+// Columns whose candidates were collected stop streaming; the finishing kernel runs their remaining levels on
+// the (<= kCandCap) candidates in shared memory.  Either way the selected keys ARE the order statistics
+// (bit-exact); the finishing kernel blends and stores.  Integer counting only: the result does not depend on
+// grid size, row split or arrival order.  HBM-bound: passes x S x T x 8 bytes.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,9 +28,17 @@ namespace rvlp {
 
 constexpr int kColBlock = 8;              // adjacent columns per CTA: 64-byte row segments
 constexpr int kBandThreads = 256;
+constexpr int kBandWarps = kBandThreads / 32;
 constexpr int kRowsPerIter = kBandThreads / kColBlock;
 constexpr int kMaxTargets = 2 * RVLP_MAX_PERCENTILES;
 constexpr int kLevels = 8;
+constexpr int kCandCap = 1024;            // candidate doubles per column
+#ifndef RVLP_BAND_UNROLL
+#define RVLP_BAND_UNROLL 8
+#endif
+#ifndef RVLP_BAND_UNROLL0      // level 0 is pure streaming + a run-length counter: more loads in flight
+#define RVLP_BAND_UNROLL0 8
+#endif
 
 struct BandTargets {                      // host-resolved numpy index arithmetic (see rvlp_capi.cu)
   int n_q;
@@ -35,32 +46,44 @@ struct BandTargets {                      // host-resolved numpy index arithmeti
   double gamma[RVLP_MAX_PERCENTILES];
 };
 
-// Workspace layout (all per column c in [0, T)), R = 2 n_q targets:
-//   hist   [3][T][R][256] uint32   ping-pong-pong histograms (level L fills L%3, reads (L-1)%3, clears (L+1)%3)
-//   prefix [2][T][R]      uint64   key prefix found so far (level L writes L%2, reads (L-1)%2)
-//   rank   [2][T][R]      uint32   remaining 0-based rank among the elements matching the prefix
+// Workspace (per column c in [0, T)), R = 2 n_q targets:
+//   hist   [3][T][R][256] uint32   level L fills L%3, launch L+1 reads it, launch L clears (L+1)%3
+//   prefix [9][T][R]      uint64   prefix[L] = the L leading digits of each target's key
+//   rank   [9][T][R]      uint32   remaining 0-based rank among the elements matching prefix[L]
+//   mode   [T]            int32    -1 streaming; L >= 1: live elements were collected by launch L
+//   ncand  [T]            uint32   candidates stored
 //   nan    [T]            uint32   column holds a NaN -> numpy returns NaN for it
+//   cand   [T][kCandCap]  double
 struct BandWorkspace {
   uint32_t* hist;
   uint64_t* prefix;
   uint32_t* rank;
+  int32_t* mode;
+  uint32_t* ncand;
   uint32_t* nan;
+  double* cand;
 };
+__host__ __device__ inline size_t band_align(size_t b) { return (b + 255) & ~(size_t)255; }
 __host__ __device__ inline size_t band_ws_bytes(int64_t T, int R) {
   size_t b = 0;
-  b += (size_t)3 * T * R * 256 * 4;
-  b += (size_t)2 * T * R * 8;
-  b += (size_t)2 * T * R * 4;
-  b += (size_t)T * 4;
-  return (b + 255) & ~(size_t)255;
+  b += band_align((size_t)3 * T * R * 256 * 4);
+  b += band_align((size_t)(kLevels + 1) * T * R * 8);
+  b += band_align((size_t)(kLevels + 1) * T * R * 4);
+  b += band_align((size_t)3 * T * 4);
+  b += band_align((size_t)T * kCandCap * 8);
+  return b;
 }
 __host__ __device__ inline BandWorkspace band_ws_carve(void* base, int64_t T, int R) {
   BandWorkspace W;
   unsigned char* p = reinterpret_cast<unsigned char*>(base);
-  W.hist = reinterpret_cast<uint32_t*>(p); p += (size_t)3 * T * R * 256 * 4;
-  W.prefix = reinterpret_cast<uint64_t*>(p); p += (size_t)2 * T * R * 8;
-  W.rank = reinterpret_cast<uint32_t*>(p); p += (size_t)2 * T * R * 4;
-  W.nan = reinterpret_cast<uint32_t*>(p);
+  W.hist = reinterpret_cast<uint32_t*>(p); p += band_align((size_t)3 * T * R * 256 * 4);
+  W.prefix = reinterpret_cast<uint64_t*>(p); p += band_align((size_t)(kLevels + 1) * T * R * 8);
+  W.rank = reinterpret_cast<uint32_t*>(p); p += band_align((size_t)(kLevels + 1) * T * R * 4);
+  W.mode = reinterpret_cast<int32_t*>(p);
+  W.ncand = reinterpret_cast<uint32_t*>(p) + T;           // ncand | nan are cleared with one memset
+  W.nan = reinterpret_cast<uint32_t*>(p) + 2 * T;
+  p += band_align((size_t)3 * T * 4);
+  W.cand = reinterpret_cast<double*>(p);
   return W;
 }
 
@@ -73,6 +96,8 @@ __device__ __forceinline__ double value_of(uint64_t k) {
   const uint64_t b = (k & 0x8000000000000000ull) ? (k ^ 0x8000000000000000ull) : ~k;
   return __longlong_as_double((long long)b);
 }
+// the L leading digits of a key (L in 0..8)
+__device__ __forceinline__ uint64_t key_head(uint64_t k, int L) { return L == 0 ? 0ull : k >> (64 - 8 * L); }
 
 // numpy/lib/_function_base_impl.py `_lerp`: a + (b - a) t, replaced by b - (b - a)(1 - t) where t >= 0.5;
 // every operation rounded separately (no FMA), as numpy's ufunc loops do.
@@ -82,172 +107,333 @@ __device__ __forceinline__ double numpy_lerp(double a, double b, double t) {
   return __dadd_rn(a, __dmul_rn(diff, t));
 }
 
-// smem: hist[kColBlock][R][256] | prefix[kColBlock][R] | rank | slot | n_uniq | uniq prefix / slot lists
-__host__ __device__ inline int band_smem_bytes(int R) {
-  return kColBlock * R * 256 * 4 + kColBlock * R * (8 + 4 + 4 + 8 + 4) + kColBlock * 4 + 16;
+// Given a 256-bin histogram spread over a warp (lane holds bins 8 lane .. 8 lane + 7), find the bin holding
+// 0-based rank rk: returns the digit, the rank inside the bin and the bin's count (all lanes get the result).
+__device__ __forceinline__ void warp_pick_bin(const uint32_t (&cnt)[8], uint32_t rk, int lane, int& digit,
+                                              uint32_t& newrank, uint32_t& bincount) {
+  uint32_t mine = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) mine += cnt[q];
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  const uint32_t excl = incl - mine;
+  const bool here = rk >= excl && rk < incl;               // exactly one lane: the counts sum to > rk
+  int d = 0;
+  uint32_t nr = 0, bc = 0;
+  if (here) {
+    uint32_t run = excl;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (rk >= run && rk < run + cnt[q]) { d = lane * 8 + q; nr = rk - run; bc = cnt[q]; }
+      run += cnt[q];
+    }
+  }
+  const unsigned who = __ballot_sync(0xffffffffu, here);
+  const int src = who ? __ffs(who) - 1 : 0;
+  digit = __shfl_sync(0xffffffffu, d, src);
+  newrank = __shfl_sync(0xffffffffu, nr, src);
+  bincount = __shfl_sync(0xffffffffu, bc, src);
 }
 
-__global__ void __launch_bounds__(kBandThreads)
-band_level_kernel(const double* __restrict__ A, int64_t S, int64_t T, int level, BandTargets tg, BandWorkspace W,
-                  double* __restrict__ out) {
+// smem of the level kernel: hist[kColBlock][R][256] | prefix[Cb][R] | uniq prefix[Cb][R] | rank[Cb][R] |
+// bin count[Cb][R] | uniq slot[Cb][R] | n_uniq[Cb] | mode[Cb]
+// Level 0 has a single (empty) prefix per column, so it needs one histogram per column, not R.
+__host__ __device__ inline int band_hist_slots(int level, int R) { return level == 0 ? 1 : R; }
+// words between the histograms of adjacent columns: +1 so that the same digit in the 8 columns of a CTA
+// falls into 8 different banks (ncu: 41 M bank conflicts per pass without it)
+__host__ __device__ inline int band_col_stride(int level, int R) { return band_hist_slots(level, R) * 256 + 1; }
+__host__ __device__ inline int band_smem_bytes(int level, int R) {
+  return ((kColBlock * band_col_stride(level, R) * 4 + 15) & ~15) + kColBlock * R * (8 + 8 + 4 + 4 + 4) + kColBlock * 8 + 16;
+}
+constexpr int band_mode_of(int level) { return level == 0 ? 0 : (level <= 3 ? 1 : 2); }
+
+// MODE 0: level 0 (every element counts, one histogram per column, digits cluster -> run-length aggregation);
+// MODE 1: levels 1-3 (prefix and digit live in the key's high word: 32-bit classification);
+// MODE 2: levels 4-8 (64-bit; level 8 only completes the prefixes).  Rarely streams: columns are normally
+//         collected by level 3.
+#ifndef RVLP_BAND_MINB0
+#define RVLP_BAND_MINB0 4
+#endif
+#ifndef RVLP_BAND_MINB1
+#define RVLP_BAND_MINB1 3      // levels 1-3: 8 loads in flight per thread (80 registers) beat a 4th resident CTA
+#endif
+template <int MODE>
+__global__ void __launch_bounds__(kBandThreads, (MODE == 0 ? RVLP_BAND_MINB0 : RVLP_BAND_MINB1))
+band_level_kernel(const double* __restrict__ A, int64_t S, int64_t T, int level, BandTargets tg, BandWorkspace W) {
   extern __shared__ __align__(16) unsigned char bsm[];
   const int R = 2 * tg.n_q;
+  const int HS = band_hist_slots(level, R);
+  const int CS = band_col_stride(level, R);
   uint32_t* hist_s = reinterpret_cast<uint32_t*>(bsm);
-  uint64_t* prefix_s = reinterpret_cast<uint64_t*>(hist_s + kColBlock * R * 256);
+  uint64_t* prefix_s = reinterpret_cast<uint64_t*>(bsm + ((kColBlock * CS * 4 + 15) & ~15));
   uint64_t* uprefix_s = prefix_s + kColBlock * R;
   uint32_t* rank_s = reinterpret_cast<uint32_t*>(uprefix_s + kColBlock * R);
-  int* slot_s = reinterpret_cast<int*>(rank_s + kColBlock * R);      // target -> target whose histogram it shares
-  int* uslot_s = slot_s + kColBlock * R;                             // unique list: histogram slot
+  uint32_t* binc_s = rank_s + kColBlock * R;               // elements matching the target's new prefix
+  int* uslot_s = reinterpret_cast<int*>(binc_s + kColBlock * R);
   int* nuniq_s = uslot_s + kColBlock * R;
+  int* mode_s = nuniq_s + kColBlock;                       // -1 stream + count, -2 nothing to do, L collect now
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t c0 = (int64_t)blockIdx.x * kColBlock;
   const int ncol = (int)min((int64_t)kColBlock, T - c0);
   const bool writer = blockIdx.y == 0;
 
-  // ---- 1. extend the prefixes by the digit the previous level's histogram selects
+  // columns collected by an EARLIER launch are finished as far as this kernel is concerned (a value equal to
+  // `level` can only be this launch's own writer CTA racing ahead: recompute, the decision is the same)
+  if (tid < kColBlock) {
+    int m = -2;
+    if (tid < ncol) {
+      const int g = W.mode[c0 + tid];
+      m = (g >= 0 && g < level) ? -2 : -1;
+    }
+    mode_s[tid] = m;
+  }
+  __syncthreads();
+  {
+    bool any = false;
+    for (int c = 0; c < ncol; ++c) any |= mode_s[c] == -1;
+    if (!any) return;                                      // CTA-uniform
+  }
+
+  // ---- 1. prefix[level] from prefix[level-1] + hist[level-1]
   if (level == 0) {
     for (int i = tid; i < kColBlock * R; i += kBandThreads) {
       prefix_s[i] = 0;
       rank_s[i] = tg.k[i % R];
-      slot_s[i] = 0;
+      binc_s[i] = (uint32_t)S;
     }
   } else {
     const uint32_t* hprev = W.hist + (size_t)((level - 1) % 3) * T * R * 256;
-    const uint64_t* pprev = W.prefix + (size_t)((level - 1) & 1) * T * R;
-    const uint32_t* rprev = W.rank + (size_t)((level - 1) & 1) * T * R;
-    for (int i = warp; i < ncol * R; i += kBandThreads / 32) {
+    const uint64_t* pprev = W.prefix + (size_t)(level - 1) * T * R;
+    const uint32_t* rprev = W.rank + (size_t)(level - 1) * T * R;
+    for (int i = warp; i < ncol * R; i += kBandWarps) {
       const int c = i / R, r = i - c * R;
+      if (mode_s[c] != -1) continue;                       // warp-uniform
       const size_t g = (size_t)(c0 + c) * R;
-      uint64_t pre;
-      uint32_t rk;
+      const uint64_t pre = pprev[g + r];
       int slot = r;
-      if (level == 1) {
-        pre = 0; rk = tg.k[r]; slot = 0;
-      } else {
-        pre = pprev[g + r]; rk = rprev[g + r];
-        for (int q = 0; q < r; ++q)                      // first target with the same prefix owns the histogram
-          if (pprev[g + q] == pre) { slot = q; break; }
-      }
+      for (int q = 0; q < r; ++q)                          // first target with the same prefix owns the histogram
+        if (pprev[g + q] == pre) { slot = q; break; }
       const uint32_t* h = hprev + (g + slot) * 256 + lane * 8;
       const uint4 v0 = *reinterpret_cast<const uint4*>(h), v1 = *reinterpret_cast<const uint4*>(h + 4);
       const uint32_t cnt[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-      uint32_t mine = 0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) mine += cnt[q];
-      uint32_t incl = mine;                              // inclusive warp scan of the 32 lane sums
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += up;
-      }
-      const uint32_t excl = incl - mine;
-      const bool here = rk >= excl && rk < incl;         // exactly one lane (counts sum to >= rk + 1)
-      int digit = 0;
-      uint32_t newrank = 0;
-      if (here) {
-        uint32_t run = excl;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          if (rk >= run && rk < run + cnt[q]) { digit = lane * 8 + q; newrank = rk - run; }
-          run += cnt[q];
-        }
-      }
-      const unsigned who = __ballot_sync(0xffffffffu, here);
-      const int src = who ? __ffs(who) - 1 : 0;
-      digit = __shfl_sync(0xffffffffu, digit, src);
-      newrank = __shfl_sync(0xffffffffu, newrank, src);
+      int digit;
+      uint32_t newrank, bincount;
+      warp_pick_bin(cnt, rprev[g + r], lane, digit, newrank, bincount);
       if (lane == 0) {
         prefix_s[c * R + r] = (pre << 8) | (uint64_t)digit;
         rank_s[c * R + r] = newrank;
+        binc_s[c * R + r] = bincount;
       }
     }
   }
   __syncthreads();
-  if (level >= 1 && writer) {                            // state for the next launch
-    uint64_t* pnext = W.prefix + (size_t)(level & 1) * T * R;
-    uint32_t* rnext = W.rank + (size_t)(level & 1) * T * R;
-    for (int i = tid; i < ncol * R; i += kBandThreads) {
-      pnext[(size_t)c0 * R + i] = prefix_s[i];
-      rnext[(size_t)c0 * R + i] = rank_s[i];
-    }
-  }
-  if (level == kLevels) {                                // ---- done: the prefixes are the order statistics
-    if (writer) {
-      for (int i = tid; i < ncol * tg.n_q; i += kBandThreads) {
-        const int c = i / tg.n_q, q = i - c * tg.n_q;
-        const double a = value_of(prefix_s[c * R + 2 * q]), b = value_of(prefix_s[c * R + 2 * q + 1]);
-        double v = numpy_lerp(a, b, tg.gamma[q]);
-        if (W.nan[c0 + c]) v = __longlong_as_double(0x7ff8000000000000ll);
-        out[(size_t)q * T + c0 + c] = v;
+  // unique prefixes per column (targets that agree so far share one histogram); collect-now decision
+  if (tid < ncol && mode_s[tid] == -1) {
+    int n = 0;
+    uint32_t live = 0;
+    for (int r = 0; r < R; ++r) {
+      bool first = true;
+      for (int q = 0; q < r; ++q)
+        if (prefix_s[tid * R + q] == prefix_s[tid * R + r]) { first = false; break; }
+      if (first) {
+        uprefix_s[tid * R + n] = prefix_s[tid * R + r];
+        uslot_s[tid * R + n] = r;
+        live += binc_s[tid * R + r];
+        ++n;
       }
     }
-    return;
-  }
-  // unique prefixes per column (targets that agree so far share one histogram)
-  if (tid < ncol) {
-    int n = 0;
-    for (int r = 0; r < R; ++r) {
-      int slot = r;
-      for (int q = 0; q < r; ++q)
-        if (prefix_s[tid * R + q] == prefix_s[tid * R + r]) { slot = q; break; }
-      slot_s[tid * R + r] = slot;
-      if (slot == r) { uprefix_s[tid * R + n] = prefix_s[tid * R + r]; uslot_s[tid * R + n] = r; ++n; }
-    }
     nuniq_s[tid] = n;
+    if (level >= 1 && live <= (uint32_t)kCandCap) mode_s[tid] = level;
   }
-  for (int i = tid; i < kColBlock * R * 256; i += kBandThreads) hist_s[i] = 0;
-  if (writer) {                                          // clear the buffer the NEXT level accumulates into
+  for (int i = tid; i < kColBlock * CS; i += kBandThreads) hist_s[i] = 0;
+  __syncthreads();
+  if (writer) {
+    uint64_t* pout = W.prefix + (size_t)level * T * R;
+    uint32_t* rout = W.rank + (size_t)level * T * R;
+    for (int i = tid; i < ncol * R; i += kBandThreads) {
+      if (mode_s[i / R] == -2) continue;
+      pout[(size_t)c0 * R + i] = prefix_s[i];
+      rout[(size_t)c0 * R + i] = rank_s[i];
+    }
+    if (tid < ncol && mode_s[tid] >= 0) W.mode[c0 + tid] = mode_s[tid];
+    // clear the buffer the NEXT level accumulates into (last read by launch level-1)
     uint32_t* hclr = W.hist + (size_t)((level + 1) % 3) * T * R * 256 + (size_t)c0 * R * 256;
     for (int i = tid; i < ncol * R * 256; i += kBandThreads) hclr[i] = 0;
   }
-  __syncthreads();
+  if (level == kLevels) return;                            // launch 8 only completes the prefixes
 
-  // ---- 2. one pass over this CTA's slab of rows
+  // ---- 2. one pass over this CTA's slab of rows (software-pipelined: the next U loads are in flight while
+  //         the current U elements are classified)
   const int c = tid % kColBlock, rl = tid / kColBlock;
   const int64_t rows_per = (S + gridDim.y - 1) / gridDim.y;
   const int64_t r_begin = (int64_t)blockIdx.y * rows_per, r_end = min(S, r_begin + rows_per);
-  const int shift = 56 - 8 * level;
   bool saw_nan = false;
-  if (c < ncol) {
+  const int my_mode = c < ncol ? mode_s[c] : -2;
+  if (my_mode != -2) {
     const int nu = nuniq_s[c];
     const double* col = A + c0 + c;
-    uint32_t* hc = hist_s + c * R * 256;
+    uint32_t* hc = hist_s + c * CS;
     const uint64_t* up = uprefix_s + c * R;
     const int* us = uslot_s + c * R;
-    constexpr int U = 4;
-    for (int64_t r = r_begin + rl; r < r_end; r += (int64_t)kRowsPerIter * U) {
-      double x[U];
+    constexpr int U = MODE == 0 ? RVLP_BAND_UNROLL0 : RVLP_BAND_UNROLL;
+    const int64_t step = (int64_t)kRowsPerIter * U;
+    int run_bin = -1;                                      // MODE 0: run-length aggregation of the digit
+    uint32_t run_len = 0;
+    auto collect = [&](double x) {                         // <= kCandCap live elements in this column
+      const uint32_t at = atomicAdd(W.ncand + c0 + c, 1u);
+      W.cand[(size_t)(c0 + c) * kCandCap + at] = x;
+    };
+    // MODE 1: the first kRegPrefix unique prefixes sit in registers behind a 32-bit Bloom mask over the low
+    // 5 bits of the candidate's head (most elements match nothing and leave after two instructions)
+    constexpr int kRegPrefix = 6;
+    uint32_t pr[kRegPrefix];
+    int sl[kRegPrefix];
+    uint32_t bloom = 0;
+    if (MODE == 1) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t rr = r + (int64_t)u * kRowsPerIter;
-        x[u] = rr < r_end ? __ldcs(col + rr * T) : 0.0;
+      for (int q = 0; q < kRegPrefix; ++q) {
+        pr[q] = q < nu ? (uint32_t)up[q] : 0xffffffffu;    // heads have <= 24 bits: all-ones never matches
+        sl[q] = q < nu ? us[q] * 256 : 0;
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (r + (int64_t)u * kRowsPerIter >= r_end) break;
-        const uint64_t k = key_of(x[u]);
-        const int digit = (int)((k >> shift) & 255u);
-        if (level == 0) {
-          saw_nan |= x[u] != x[u];
-          atomicAdd(hc + digit, 1u);
+      for (int q = 0; q < nu; ++q) bloom |= 1u << ((uint32_t)up[q] & 31u);
+    }
+    const int hs = 32 - 8 * level, ds = 24 - 8 * level, shift = 56 - 8 * level;
+    auto classify = [&](double x) {
+      if (MODE == 0) {                                     // digit 0 of every element; only the high word matters
+        saw_nan |= x != x;
+        const uint32_t hw = (uint32_t)__double2hiint(x);
+        const uint32_t k = hw ^ ((uint32_t)((int32_t)hw >> 31) | 0x80000000u);
+        const int bin = (int)(k >> 24);
+        if (bin == run_bin) {
+          ++run_len;
         } else {
-          const uint64_t hi = k >> (shift + 8);
-          for (int q = 0; q < nu; ++q)
-            if (hi == up[q]) atomicAdd(hc + us[q] * 256 + digit, 1u);
+          if (run_len) atomicAdd(hc + run_bin, run_len);
+          run_bin = bin;
+          run_len = 1;
+        }
+      } else if (MODE == 1) {
+        const uint32_t hw = (uint32_t)__double2hiint(x);
+        const uint32_t k = hw ^ ((uint32_t)((int32_t)hw >> 31) | 0x80000000u);
+        const uint32_t hi = k >> hs;
+        if ((bloom >> (hi & 31u)) & 1u) {
+          int slot = -1;
+#pragma unroll
+          for (int q = 0; q < kRegPrefix; ++q)
+            if (hi == pr[q]) slot = sl[q];
+          for (int q = kRegPrefix; q < nu; ++q)
+            if (hi == (uint32_t)up[q]) slot = us[q] * 256;
+          if (slot >= 0) {
+            if (my_mode >= 0) collect(x);
+            else atomicAdd(hc + slot + (int)((k >> ds) & 255u), 1u);
+          }
+        }
+      } else {
+        const uint64_t k = key_of(x);
+        const uint64_t hi = key_head(k, level);
+        int slot = -1;
+        for (int q = 0; q < nu; ++q)
+          if (hi == up[q]) { slot = us[q] * 256; break; }
+        if (slot >= 0) {
+          if (my_mode >= 0) collect(x);
+          else atomicAdd(hc + slot + (int)((k >> shift) & 255u), 1u);
         }
       }
+    };
+    // full iterations: no bounds checks; the next U loads are issued before the current U are classified
+    const int64_t first = r_begin + rl;
+    const int64_t n_full = first + (U - 1) * kRowsPerIter < r_end ? (r_end - first - (U - 1) * kRowsPerIter + step - 1) / step : 0;
+    const double* ptr = col + first * T;
+    const int64_t dstep = step * T, drow = (int64_t)kRowsPerIter * T;
+    double cur[U], nxt[U];
+    if (n_full > 0) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) cur[u] = __ldcs(ptr + u * drow);
+      for (int64_t it = 1; it < n_full; ++it) {
+        ptr += dstep;
+#pragma unroll
+        for (int u = 0; u < U; ++u) nxt[u] = __ldcs(ptr + u * drow);
+#pragma unroll
+        for (int u = 0; u < U; ++u) classify(cur[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) classify(cur[u]);
     }
+    for (int64_t r = first + n_full * step; r < r_end; r += kRowsPerIter) classify(__ldcs(col + r * T));   // tail
+    if (MODE == 0 && run_len) atomicAdd(hc + run_bin, run_len);
   }
   if (saw_nan) atomicOr(W.nan + c0 + c, 1u);
   __syncthreads();
   // ---- 3. merge into the level's global histogram
   uint32_t* hcur = W.hist + (size_t)(level % 3) * T * R * 256 + (size_t)c0 * R * 256;
-  for (int i = tid; i < ncol * R * 256; i += kBandThreads) {
-    const uint32_t v = hist_s[i];
-    if (v) atomicAdd(hcur + i, v);
+  for (int i = tid; i < ncol * HS * 256; i += kBandThreads) {
+    const int cc = i / (HS * 256), w = i - cc * (HS * 256);
+    const uint32_t v = hist_s[cc * CS + w];
+    if (v) atomicAdd(hcur + cc * (R * 256) + w, v);
   }
 }
 
+// Finishing kernel: one warp per column.  Streaming columns have complete keys in prefix[8]; collected columns
+// run their remaining levels on the candidates (cached in shared memory).  Then numpy's blend.
+constexpr int kFinishSmem = kBandWarps * (kCandCap * 8 + 256 * 4);
+__global__ void __launch_bounds__(kBandThreads)
+band_finish_kernel(int64_t T, BandTargets tg, BandWorkspace W, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char bsm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* cand_s = reinterpret_cast<double*>(bsm) + warp * kCandCap;
+  uint32_t* hist_w = reinterpret_cast<uint32_t*>(bsm + kBandWarps * kCandCap * 8) + warp * 256;
+  const int R = 2 * tg.n_q;
+  const int64_t c = (int64_t)blockIdx.x * kBandWarps + warp;
+  if (c >= T) return;
+  const int mode = W.mode[c];
+  const int L0 = mode >= 0 ? mode : kLevels;
+  uint32_t n = 0;
+  if (mode >= 0) {
+    n = W.ncand[c];
+    for (uint32_t i = lane; i < n; i += 32) cand_s[i] = W.cand[(size_t)c * kCandCap + i];
+    __syncwarp();
+  }
+  const uint64_t* pre = W.prefix + (size_t)L0 * T * R + (size_t)c * R;
+  const uint32_t* rk0 = W.rank + (size_t)L0 * T * R + (size_t)c * R;
+  for (int q = 0; q < tg.n_q; ++q) {
+    double v[2];
+    for (int h = 0; h < 2; ++h) {
+      const int r = 2 * q + h;
+      uint64_t p = pre[r];
+      uint32_t rk = rk0[r];
+      for (int L = L0; L < kLevels; ++L) {                 // collected columns only
+        for (int i = lane; i < 256; i += 32) hist_w[i] = 0;
+        __syncwarp();
+        const int shift = 56 - 8 * L;
+        for (uint32_t i = lane; i < n; i += 32) {
+          const uint64_t k = key_of(cand_s[i]);
+          if (key_head(k, L) == p) atomicAdd(&hist_w[(k >> shift) & 255u], 1u);
+        }
+        __syncwarp();
+        uint32_t cnt[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cnt[j] = hist_w[lane * 8 + j];
+        int digit;
+        uint32_t newrank, bincount;
+        warp_pick_bin(cnt, rk, lane, digit, newrank, bincount);
+        p = (p << 8) | (uint64_t)digit;
+        rk = newrank;
+        __syncwarp();
+      }
+      v[h] = value_of(p);
+    }
+    if (lane == 0) {
+      double res = numpy_lerp(v[0], v[1], tg.gamma[q]);
+      if (W.nan[c]) res = __longlong_as_double(0x7ff8000000000000ll);
+      out[(size_t)q * T + c] = res;
+    }
+  }
+}
 
 }  // namespace rvlp

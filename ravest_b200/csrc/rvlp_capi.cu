@@ -490,27 +490,39 @@ int rvlp_percentile_columns(const double* A_dev, int64_t S, int64_t T, const dou
   }
   const BandWorkspace W = band_ws_carve(ws_dev, T, R);
   CUDA_TRY(cudaMemsetAsync(W.hist, 0, (size_t)T * R * 256 * 4, st));   // level 0 accumulates into buffer 0
-  CUDA_TRY(cudaMemsetAsync(W.nan, 0, (size_t)T * 4, st));
-  const int smem = band_smem_bytes(R);
+  CUDA_TRY(cudaMemsetAsync(W.mode, 0xff, (size_t)T * 4, st));          // -1: every column streams
+  CUDA_TRY(cudaMemsetAsync(W.ncand, 0, (size_t)2 * T * 4, st));        // candidate counters + NaN flags
   static bool attr_done = false;
   if (!attr_done) {
-    CUDA_TRY(cudaFuncSetAttribute(band_level_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(kMaxTargets)));
+    CUDA_TRY(cudaFuncSetAttribute(band_level_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(1, kMaxTargets)));
+    CUDA_TRY(cudaFuncSetAttribute(band_level_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(1, kMaxTargets)));
+    CUDA_TRY(cudaFuncSetAttribute(band_level_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(1, kMaxTargets)));
+    CUDA_TRY(cudaFuncSetAttribute(band_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinishSmem));
     attr_done = true;
   }
   int sms = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const int64_t ncb = (T + kColBlock - 1) / kColBlock;
-  // row split: ~4 CTAs per SM in total, but at least 2048 rows per CTA so that the per-CTA scan / merge stays small
-  int64_t split = (4 * (int64_t)sms + ncb - 1) / ncb;
-  const int64_t max_split = (S + 2047) / 2048;
-  if (split > max_split) split = max_split;
-  if (split < 1) split = 1;
-  if (split > 65535) split = 65535;
   for (int level = 0; level <= kLevels; ++level) {
+    // Row split: every CTA does the same amount of work, so the grid is sized to ONE wave of resident CTAs
+    // (a 1.06-wave grid costs two full rounds); at least 1024 rows per CTA keeps the per-CTA scan / merge small.
+    const int smem = band_smem_bytes(level, R);
+    int per_sm = 0;
+    void (*kern)(const double*, int64_t, int64_t, int, BandTargets, BandWorkspace) =
+        band_mode_of(level) == 0 ? band_level_kernel<0> : (band_mode_of(level) == 1 ? band_level_kernel<1> : band_level_kernel<2>);
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBandThreads, smem));
+    if (per_sm < 1) return fail(RVLP_EUNSUPPORTED, "band kernel does not fit on an SM");
+    int64_t split = (int64_t)sms * per_sm / ncb;
+    const int64_t max_split = (S + 1023) / 1024;
+    if (split > max_split) split = max_split;
+    if (split < 1) split = 1;
+    if (split > 65535) split = 65535;
     const dim3 grid((unsigned)ncb, level == kLevels ? 1u : (unsigned)split);
-    band_level_kernel<<<grid, kBandThreads, smem, st>>>(A_dev, S, T, level, tg, W, out_dev);
+    kern<<<grid, kBandThreads, smem, st>>>(A_dev, S, T, level, tg, W);
     ++g_launches;
   }
+  band_finish_kernel<<<(unsigned)((T + kBandWarps - 1) / kBandWarps), kBandThreads, kFinishSmem, st>>>(T, tg, W, out_dev);
+  ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return RVLP_OK;
 }
