@@ -88,6 +88,8 @@ int simple_grid(int64_t n) {
 
 }  // namespace
 
+constexpr int kTicketRing = 256;   // launches in flight per context before a counter is reused
+
 struct rvlp_ctx {
   int device = 0;
   DevProblem P{};
@@ -103,6 +105,8 @@ struct rvlp_ctx {
   double* d_theta = nullptr;
   double* d_out = nullptr;
   int64_t cap_samples = 0;
+  unsigned long long* d_tickets = nullptr;   // ring of batch-ticket counters for logprob_kernel's dynamic schedule
+  std::atomic<unsigned> ticket_slot{0};
   cudaStream_t stream = nullptr;    // host-buffer path: chunks alternate between two streams so that
   cudaStream_t stream2 = nullptr;   // the H2D copy of chunk i+1 overlaps the kernel of chunk i
 };
@@ -223,6 +227,7 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_blocked_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   }
+  CTX_TRY(cudaMalloc((void**)&c->d_tickets, sizeof(unsigned long long) * kTicketRing));
   CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CTX_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
 #undef CTX_TRY
@@ -239,6 +244,7 @@ void rvlp_ctx_destroy(rvlp_ctx* c) {
   cudaFree(c->d_priors);
   cudaFree(c->d_theta);
   cudaFree(c->d_out);
+  cudaFree(c->d_tickets);
   if (c->h_theta) cudaFreeHost(c->h_theta);
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -257,7 +263,12 @@ static int launch_logprob(rvlp_ctx* c, const double* theta, int64_t S, double* o
   const int nb = (int)(per_warp >= kG ? kG : (per_warp < 1 ? 1 : per_warp));
   const int64_t want = ((S + nb - 1) / nb + kWarps - 1) / kWarps;
   if (want < grid) grid = (int)want;
-  logprob_kernel<<<grid, kThreads, c->smem_main, st>>>(c->P, theta, S, out, ll, lp, nb);
+  unsigned long long* tickets = nullptr;
+  if (per_warp >= 2) {                                     // several batches per warp: dynamic schedule
+    tickets = c->d_tickets + (c->ticket_slot.fetch_add(1) % kTicketRing);
+    CUDA_TRY(cudaMemsetAsync(tickets, 0, sizeof(unsigned long long), st));
+  }
+  logprob_kernel<<<grid, kThreads, c->smem_main, st>>>(c->P, theta, S, out, ll, lp, nb, tickets);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return RVLP_OK;
@@ -309,11 +320,25 @@ int rvlp_logprob_batch_host(rvlp_ctx* c, const double* theta_host, int64_t S, do
   double* dst = out_pinned ? out_host : c->h_out;
   // chunked, chunks alternating between two streams: the H2D of chunk i+1 (and the staging memcpy) overlaps
   // the kernel of chunk i, the D2H of chunk i overlaps the kernel of chunk i+1
-  const int64_t chunk = S > (1 << 16) ? (S + 7) / 8 : S;
-  int ci = 0;
-  for (int64_t s0 = 0; s0 < S; s0 += chunk, ++ci) {
+  // Growing chunks (1/16, 1/16, 1/8, 1/4, 1/2 of the rows): the first copy that nothing can hide is small, every
+  // later copy is shorter than the kernel it hides behind, and few launches mean few tails.
+  int64_t bounds[8];
+  int nchunks = 0;
+  if (S > (1 << 16)) {
+    const int64_t unit = ((S + 15) / 16 + 3) & ~(int64_t)3;
+    const int mult[5] = {1, 1, 2, 4, 8};
+    int64_t at = 0;
+    for (int i = 0; i < 5 && at < S; ++i) {
+      at += unit * mult[i];
+      bounds[nchunks++] = at < S && i < 4 ? at : S;
+    }
+  } else {
+    bounds[nchunks++] = S;
+  }
+  int64_t s0 = 0;
+  for (int ci = 0; ci < nchunks; s0 = bounds[ci], ++ci) {
     cudaStream_t st = (ci & 1) ? c->stream2 : c->stream;
-    const int64_t n = (S - s0 < chunk) ? S - s0 : chunk;
+    const int64_t n = bounds[ci] - s0;
     const size_t off = (size_t)s0 * (size_t)c->P.ndim;
     const size_t nbytes = sizeof(double) * (size_t)n * (size_t)c->P.ndim;
     if (!in_pinned) memcpy(c->h_theta + off, theta_host + off, nbytes);

@@ -455,7 +455,8 @@ __device__ __forceinline__ void sample_chi_pipelined(const DevProblem& P, const 
 // ------------------------------------------------------------------ K1: log-probability
 __global__ void __launch_bounds__(kThreads, RVLP_MIN_BLOCKS)
 logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double* __restrict__ out,
-               double* __restrict__ ll_out, double* __restrict__ lp_out, int nb) {
+               double* __restrict__ ll_out, double* __restrict__ lp_out, int nb,
+               unsigned long long* __restrict__ next_batch) {
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = smem_layout(P);
   stage_problem(P, L, smem);
@@ -471,8 +472,18 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
   if ((warp >> 2) & 1) __nanosleep(RVLP_STAGGER_NS);
 #endif
 
-  for (int64_t b = gw; b < n_batches; b += nw) {
+  // Every warp starts on batch `gw`; further batches come from a global ticket counter when the launch has
+  // several batches per warp (no quantisation tail: 13.2 batches per warp would otherwise cost 14), or from a
+  // static stride for small launches.  Which warp evaluates a sample never changes its bits.
+  for (int64_t b = gw; b < n_batches;) {
     const int64_t s0 = b * nb;
+    if (next_batch) {
+      unsigned long long t = 0;
+      if (lane == 0) t = atomicAdd(next_batch, 1ull);
+      b = nw + (int64_t)__shfl_sync(0xffffffffu, t, 0);
+    } else {
+      b += nw;
+    }
     sample_prologue(P, T, theta, s0, S, scratch, rec, lane, true, nb);
     for (int g = 0; g < nb; ++g) {
       const int64_t s = s0 + g;
