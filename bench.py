@@ -174,6 +174,49 @@ def time_kernel(torch, fn, steps: int, warmup: int, barrier) -> float:
     return a.elapsed_time(b)
 
 
+def sample_matrix_rows(torch, fit, barrier) -> dict:
+    """SURVEY.md §8 rows f-1..f-4 on one GPU: per-sample RV matrix (K2), percentile bands (K6), walker checks
+    (K5), GP conditioning (K7).  HBM-bound rows are quoted against MEASURED_PEAKS.json's copy bandwidth."""
+    from ravest_b200 import _lib, workloads
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "MEASURED_PEAKS.json"
+    except Exception:
+        hbm, hbm_src = 6550.0, "fallback (B200_PROFILING.md)"
+    res = {"hbm_peak_gbs": hbm, "hbm_peak_source": hbm_src}
+    spec, theta = workloads.make_c2(100_000)
+    post = fit.from_spec(spec)
+    th = torch.as_tensor(theta, device="cuda")
+    S, T = len(theta), 1000
+    times = torch.linspace(float(spec["time"].min()), float(spec["time"].max()), T, dtype=torch.float64, device="cuda")
+    m = torch.empty((S, T), dtype=torch.float64, device="cuda")
+    ms = time_kernel(torch, lambda: post.ctx.rv_matrix(th, times, -2, out=m), 5, 2, barrier) / 5
+    res["f1_rv_matrix"] = {"shape": f"c2 posterior: {S} samples x {T} times x 2 planets", "ms": ms,
+                           "evals_per_s": S * T * 2 / ms * 1e3, "write_gbs": S * T * 8 / ms / 1e6}
+    out = torch.empty((3, T), dtype=torch.float64, device="cuda")
+    ms = time_kernel(torch, lambda: _lib.percentile_columns(m, [15.85, 50, 84.15], out=out), 5, 2, barrier) / 5
+    res["f2_percentile_bands"] = {"shape": f"{S} x {T} fp64 matrix ({S * T * 8 / 1e6:.0f} MB), q = [15.85, 50, 84.15]",
+                                  "ms": ms, "streaming_passes": 4, "achieved_gbs": 4 * S * T * 8 / ms / 1e6,
+                                  "frac_of_hbm_peak": 4 * S * T * 8 / ms / 1e6 / hbm,
+                                  "matrix_reads_per_s_gbs": S * T * 8 / ms / 1e6}
+    del m
+    spec3, theta3 = workloads.make_c3(1_000_000)
+    post3 = fit.from_spec(spec3)
+    th3 = torch.as_tensor(theta3, device="cuda")
+    ms = time_kernel(torch, lambda: post3.ctx.walker_check(th3), 5, 2, barrier) / 5
+    res["f3_walker_check"] = {"shape": "c3: 1e6 candidate rows x 29 columns", "ms": ms, "rows_per_s": 1e6 / ms * 1e3,
+                              "read_gbs": theta3.nbytes / ms / 1e6}
+    del th3, post3
+    spec5, theta5 = workloads.make_c5(10_000)
+    post5 = fit.from_spec(spec5)
+    th5 = torch.as_tensor(theta5, device="cuda")
+    t5 = torch.linspace(float(spec5["time"].min()), float(spec5["time"].max()), T, dtype=torch.float64, device="cuda")
+    ms = time_kernel(torch, lambda: post5.ctx.gp_predict(th5, t5), 3, 1, barrier) / 3
+    res["f4_gp_conditioning"] = {"shape": f"c5: 1e4 samples x {len(spec5['time'])} epochs -> {T} test times", "ms": ms,
+                                 "samples_per_s": 1e4 / ms * 1e3}
+    return res
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -275,8 +318,13 @@ def main() -> None:
                     traffic = tj["dram_bytes_per_launch"]
             except Exception:
                 traffic = None
+            hw = None
+            try:      # hardware view of the same launch shape from the committed ncu capture
+                hw = json.load(open(os.path.join(ROOT, "profiles", "r01_hw.json"))).get(name)
+            except Exception:
+                hw = None
             roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_flops / 1e12, "unit": "TFLOP/s",
-                        "frac": achieved / (peak_flops / 1e12), "traffic": traffic,
+                        "frac": achieved / (peak_flops / 1e12), "traffic": traffic, "hw": hw,
                         "peak_source": "measured live: dependent-free DFMA kernel (rvlp_measure_fp64_peak), burst",
                         "flops_per_unit": fpu, "kernel": "rvlp::logprob_kernel",
                         "kernel_ms_per_launch": ms_kernel / args.steps,
@@ -323,6 +371,10 @@ def main() -> None:
                 except Exception as ex:       # report, never hide
                     others[other] = {"error": repr(ex)}
             line["other_workloads"] = others
+            try:
+                line["sample_matrix_rows"] = sample_matrix_rows(torch, fit, barrier)
+            except Exception as ex:           # report, never hide
+                line["sample_matrix_rows"] = {"error": repr(ex)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -382,8 +382,13 @@ int rvlp_rv_batch_frozen(rvlp_ctx* c, const double* theta_dev, int64_t S, const 
   const int64_t want = ((S + kG - 1) / kG + kWarps - 1) / kWarps;
   int rc = grid_for(c->device, (const void*)rv_matrix_kernel, c->smem_main, want, &grid);
   if (rc) return rc;
+  unsigned long long* tickets = nullptr;
+  if (want >= 2 * (int64_t)grid) {                           // several batches per warp: dynamic schedule
+    tickets = c->d_tickets + (c->ticket_slot.fetch_add(1) % kTicketRing);
+    CUDA_TRY(cudaMemsetAsync(tickets, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+  }
   rv_matrix_kernel<<<grid, kThreads, c->smem_main, (cudaStream_t)stream>>>(c->P, theta_dev, S, times_dev, T,
-                                                                           component, out_dev, frozen);
+                                                                           component, out_dev, frozen, tickets);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return RVLP_OK;

@@ -535,7 +535,7 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
 __global__ void __launch_bounds__(kThreads, RVLP_MIN_BLOCKS)
 rv_matrix_kernel(DevProblem P, const double* __restrict__ theta, int64_t S,
                  const double* __restrict__ times, int64_t T_n, int component, double* __restrict__ out,
-                 FrozenParams frozen) {
+                 FrozenParams frozen, unsigned long long* __restrict__ next_batch) {
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = smem_layout(P);
   stage_problem(P, L, smem);
@@ -549,8 +549,15 @@ rv_matrix_kernel(DevProblem P, const double* __restrict__ theta, int64_t S,
   const int only = component >= 0 ? component : (component == RVLP_RV_TREND ? P.n_planets : -1);
   const bool trend = component < 0;
 
-  for (int64_t b = gw; b < n_batches; b += nw) {
+  for (int64_t b = gw; b < n_batches;) {
     const int64_t s0 = b * kG;
+    if (next_batch) {                                        // dynamic schedule, as in logprob_kernel
+      unsigned long long t = 0;
+      if (lane == 0) t = atomicAdd(next_batch, 1ull);
+      b = nw + (int64_t)__shfl_sync(0xffffffffu, t, 0);
+    } else {
+      b += nw;
+    }
     sample_prologue(P, T, theta, s0, S, scratch, rec, lane, false);
     for (int g = 0; g < kG; ++g) {
       const int64_t s = s0 + g;
