@@ -124,6 +124,14 @@ void rvlp_ctx_destroy(rvlp_ctx* ctx);
 int rvlp_logprob_batch(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples,
                        double* out_dev, void* stream);
 
+/* Optional, synchronous: times the compiled shapes of the log-probability kernel on (a prefix of) the caller's
+ * rows and keeps the fastest for this context; *chosen (may be NULL) gets its index.  The choice changes the
+ * speed only - every shape produces identical bits (tests/test_gpu_parity.py). */
+int rvlp_ctx_autotune(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples, int32_t* chosen);
+
+/* Diagnostic: force shape `variant` (0 or 1) of the log-probability kernel for this context. */
+int rvlp_ctx_set_variant(rvlp_ctx* ctx, int32_t variant);
+
 /* Same call for HOST buffers (what a NumPy caller such as emcee holds): pinned staging,
  * H2D of theta, kernel, D2H of out, one host synchronisation at the end. */
 int rvlp_logprob_batch_host(rvlp_ctx* ctx, const double* theta_host, int64_t n_samples,

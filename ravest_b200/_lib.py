@@ -29,7 +29,7 @@ EXPORTS = [
     "rvlp_logprob_batch_host", "rvlp_logprob_parts_batch", "rvlp_rv_batch", "rvlp_gp_logprob_batch",
     "rvlp_kepler_rv", "rvlp_planet_rv", "rvlp_trend_rv", "rvlp_convert_to_default", "rvlp_prior_eval",
     "rvlp_measure_fp64_peak", "rvlp_launch_count", "rvlp_rv_batch_frozen", "rvlp_walker_check_batch",
-    "rvlp_gp_predict_batch", "rvlp_percentile_workspace_bytes", "rvlp_percentile_columns",
+    "rvlp_gp_predict_batch", "rvlp_percentile_workspace_bytes", "rvlp_percentile_columns", "rvlp_ctx_autotune", "rvlp_ctx_set_variant",
 ]
 MAX_FROZEN = 16
 MAX_PERCENTILES = 8
@@ -90,6 +90,8 @@ def load() -> C.CDLL:
     lib.rvlp_convert_to_default.argtypes = [i32, vp, i64, vp, vp, C.c_int, vp]
     lib.rvlp_prior_eval.argtypes = [C.POINTER(PriorPOD), vp, i64, vp, C.c_int, vp]
     lib.rvlp_measure_fp64_peak.argtypes = [C.c_int, C.c_int, C.POINTER(dbl), C.POINTER(dbl)]
+    lib.rvlp_ctx_autotune.argtypes = [vp, vp, i64, C.POINTER(i32)]
+    lib.rvlp_ctx_set_variant.argtypes = [vp, i32]
     lib.rvlp_rv_batch_frozen.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp, vp, vp]
     lib.rvlp_walker_check_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     lib.rvlp_gp_predict_batch.argtypes = [vp, vp, i64, vp, i64, vp, vp, vp]
@@ -211,6 +213,7 @@ class Context:
                                   len(t), self.device, C.byref(h)))
         self._h = h
         self._lib = lib
+        self.k1_variant = None      # set by autotune()
 
     def close(self) -> None:
         if getattr(self, "_h", None):
@@ -232,9 +235,26 @@ class Context:
             raise ValueError(f"theta must have shape (S, {self.desc.ndim}), got {tuple(th.shape)}")
         return th
 
+    AUTOTUNE_MIN_ROWS = 1 << 15
+
+    def autotune(self, theta) -> int:
+        """Pick the fastest compiled shape of the log-probability kernel for this problem (synchronous, once)."""
+        th = self._theta(theta)
+        chosen = C.c_int32(0)
+        check(self._lib.rvlp_ctx_autotune(self._h, th.data_ptr(), th.shape[0], C.byref(chosen)))
+        self.k1_variant = int(chosen.value)
+        return self.k1_variant
+
+    def set_variant(self, variant: int) -> None:
+        check(self._lib.rvlp_ctx_set_variant(self._h, int(variant)))
+        self.k1_variant = int(variant)
+
     def logprob(self, theta, out=None):
         torch = _torch()
         th = self._theta(theta)
+        if (self.k1_variant is None and th.shape[0] >= self.AUTOTUNE_MIN_ROWS and not self.desc.is_gp
+                and os.environ.get("RVLP_AUTOTUNE", "1") != "0"):
+            self.autotune(th)
         if out is None:
             out = torch.empty(th.shape[0], dtype=torch.float64, device=th.device)
         fn = self._lib.rvlp_gp_logprob_batch if self.desc.is_gp else self._lib.rvlp_logprob_batch
@@ -259,6 +279,9 @@ class Context:
             raise ValueError(f"theta must have shape (S, {self.desc.ndim}), got {th.shape}")
         if out_np is None:
             out_np = np.empty(th.shape[0], dtype=np.float64)
+        if (self.k1_variant is None and th.shape[0] >= self.AUTOTUNE_MIN_ROWS and not self.desc.is_gp
+                and os.environ.get("RVLP_AUTOTUNE", "1") != "0"):
+            self.autotune(th[:1 << 16])
         check(self._lib.rvlp_logprob_batch_host(self._h, th.ctypes.data, th.shape[0], out_np.ctypes.data))
         return out_np
 

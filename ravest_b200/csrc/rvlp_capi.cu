@@ -88,6 +88,11 @@ int simple_grid(int64_t n) {
 
 }  // namespace
 
+// K1 shapes (rvlp_kernels.cuh: logprob_kernel<W, MB>); variant 0 is the default until rvlp_ctx_autotune ran
+typedef void (*k1_fn)(DevProblem, const double*, int64_t, double*, double*, double*, int, unsigned long long*);
+constexpr int kK1Variants = 2;
+static k1_fn k1_variant(int v) { return v == 1 ? logprob_kernel<2, 3> : logprob_kernel<kW, RVLP_MIN_BLOCKS>; }
+
 constexpr int kTicketRing = 256;   // launches in flight per context before a counter is reused
 
 struct rvlp_ctx {
@@ -99,6 +104,8 @@ struct rvlp_ctx {
   void* d_epochs = nullptr;
   int smem_main = 0, smem_gp = 0, smem_gp_tiled = 0, smem_gp_blocked = 0, gp_tile = 0, smem_gp_predict = 0;
   int max_smem = 0;
+  int k1 = 0;          // K1 variant in use
+  int k1_tuned = 0;    // rvlp_ctx_autotune has run
   // host-buffer path
   double* h_theta = nullptr;
   double* h_out = nullptr;
@@ -201,7 +208,8 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
     rvlp_ctx_destroy(c);
     return rc;
   }
-  CTX_TRY(cudaFuncSetAttribute(logprob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+  for (int v = 0; v < kK1Variants; ++v)
+    CTX_TRY(cudaFuncSetAttribute(k1_variant(v), cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   CTX_TRY(cudaFuncSetAttribute(rv_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   CTX_TRY(cudaFuncSetAttribute(walker_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   if (P.n_hyper) {
@@ -256,7 +264,8 @@ static int launch_logprob(rvlp_ctx* c, const double* theta, int64_t S, double* o
                           cudaStream_t st) {
   if (S == 0) return RVLP_OK;
   int grid = 0;
-  int rc = grid_for(c->device, (const void*)logprob_kernel, c->smem_main, INT_MAX, &grid);   // full wave
+  const k1_fn kern = k1_variant(c->k1);
+  int rc = grid_for(c->device, (const void*)kern, c->smem_main, INT_MAX, &grid);   // full wave
   if (rc) return rc;
   // samples per prologue batch: kG when every resident warp still gets a batch, else 1 (latency of small S)
   int64_t per_warp = S / ((int64_t)grid * kWarps);
@@ -268,7 +277,7 @@ static int launch_logprob(rvlp_ctx* c, const double* theta, int64_t S, double* o
     tickets = c->d_tickets + (c->ticket_slot.fetch_add(1) % kTicketRing);
     CUDA_TRY(cudaMemsetAsync(tickets, 0, sizeof(unsigned long long), st));
   }
-  logprob_kernel<<<grid, kThreads, c->smem_main, st>>>(c->P, theta, S, out, ll, lp, nb, tickets);
+  kern<<<grid, kThreads, c->smem_main, st>>>(c->P, theta, S, out, ll, lp, nb, tickets);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return RVLP_OK;
@@ -279,6 +288,49 @@ int rvlp_logprob_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, double* 
   if (c->P.n_hyper) return fail(RVLP_EINVAL, "GP context: call rvlp_gp_logprob_batch");
   DeviceGuard guard(c->device);
   return launch_logprob(c, theta_dev, S, out_dev, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int rvlp_ctx_set_variant(rvlp_ctx* c, int32_t variant) {
+  if (!c || variant < 0 || variant >= kK1Variants) return fail(RVLP_EINVAL, "variant must be 0..%d", kK1Variants - 1);
+  c->k1 = variant;
+  c->k1_tuned = 1;
+  return RVLP_OK;
+}
+
+int rvlp_ctx_autotune(rvlp_ctx* c, const double* theta_dev, int64_t S, int32_t* chosen) {
+  if (!c || S < 0 || (S > 0 && !theta_dev)) return fail(RVLP_EINVAL, "bad arguments");
+  if (chosen) *chosen = c->k1;
+  if (c->P.n_hyper || S < 4096) return RVLP_OK;             // nothing to choose for GP contexts / tiny batches
+  DeviceGuard guard(c->device);
+  const int64_t n = S < 65536 ? S : 65536;
+  double* scratch = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&scratch, sizeof(double) * (size_t)n));
+  cudaEvent_t a, b;
+  CUDA_TRY(cudaEventCreate(&a));
+  CUDA_TRY(cudaEventCreate(&b));
+  float best = 1e30f;
+  int best_v = 0, rc = RVLP_OK;
+  for (int v = 0; v < kK1Variants && rc == RVLP_OK; ++v) {
+    c->k1 = v;
+    float tmin = 1e30f;
+    for (int rep = 0; rep < 3 && rc == RVLP_OK; ++rep) {    // first repetition doubles as warm-up
+      cudaEventRecord(a, c->stream);
+      rc = launch_logprob(c, theta_dev, n, scratch, nullptr, nullptr, c->stream);
+      cudaEventRecord(b, c->stream);
+      if (cudaEventSynchronize(b) != cudaSuccess) rc = fail(RVLP_ECUDA, "autotune launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      float ms = 0;
+      cudaEventElapsedTime(&ms, a, b);
+      if (rep > 0 && ms < tmin) tmin = ms;
+    }
+    if (tmin < best) { best = tmin; best_v = v; }
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(scratch);
+  c->k1 = rc == RVLP_OK ? best_v : 0;
+  c->k1_tuned = 1;
+  if (chosen) *chosen = c->k1;
+  return rc;
 }
 
 int rvlp_logprob_parts_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, double* ll_dev, double* lp_dev,

@@ -453,7 +453,13 @@ __device__ __forceinline__ void sample_chi_pipelined(const DevProblem& P, const 
 }
 
 // ------------------------------------------------------------------ K1: log-probability
-__global__ void __launch_bounds__(kThreads, RVLP_MIN_BLOCKS)
+// Two shapes are compiled: <kW = 4 epochs per lane in flight, 2 CTAs/SM> and <2, 3 CTAs/SM>.  Neither wins
+// everywhere (profiles/r01_sweep8.log: W = 4 is 2-4 % ahead on the low-eccentricity 5-planet config, W = 2
+// is 10 % ahead on the high-eccentricity config and 4 % on 120-epoch data); rvlp_ctx_autotune times both on
+// the caller's own rows.  A lane visits its epochs (lane, lane + 32, ...) in ascending order for either W, so
+// the choice never changes a bit of the result.
+template <int W, int MB>
+__global__ void __launch_bounds__(kThreads, MB)
 logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double* __restrict__ out,
                double* __restrict__ ll_out, double* __restrict__ lp_out, int nb,
                unsigned long long* __restrict__ next_batch) {
@@ -503,12 +509,12 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
         } else if ((RVLP_PIPELINE & 2) && (flags & F_CLS_FULL)) {
           sample_chi_pipelined<kWP, 2, 1>(P, T, sr, lane, 2.5e-4, acc);
         } else {
-          for (int base = 0; base < P.n_pad; base += 32 * kW) {
-            double tt[kW], rv[kW];
+          for (int base = 0; base < P.n_pad; base += 32 * W) {
+            double tt[W], rv[W];
 #pragma unroll
-            for (int j = 0; j < kW; ++j) tt[j] = T.t[base + j * 32 + lane];
-            model_rv<kW>(P, sr, tt, rv, -1, true);
-            chi_epilogue<kW>(P, T, sr, base, lane, rv, acc);
+            for (int j = 0; j < W; ++j) tt[j] = T.t[base + j * 32 + lane];
+            model_rv<W>(P, sr, tt, rv, -1, true);
+            chi_epilogue<W>(P, T, sr, base, lane, rv, acc);
           }
         }
         ll = -0.5 * chi_finish(acc);

@@ -390,6 +390,26 @@ def test_bit_stability_under_sharding_and_batching(cuda):
     assert np.array_equal(host.view(np.int64), full.cpu().numpy().view(np.int64))
 
 
+def test_kernel_shapes_are_bit_identical_and_autotune_picks_one(cuda):
+    """logprob_kernel<4, 2> and <2, 3> (rvlp_ctx_autotune chooses between them) must agree bit for bit."""
+    from ravest_b200 import workloads
+    for maker, S in ((workloads.make_c3, 40_000), (workloads.make_c4, 40_000), (workloads.make_c2, 50_000)):
+        spec, theta = maker(S)
+        th = cuda.as_tensor(theta, device="cuda")
+        outs = []
+        for v in (0, 1):
+            post = _post(spec)
+            post.ctx.set_variant(v)
+            outs.append(post.ctx.logprob(th).cpu().numpy())
+        assert np.array_equal(outs[0].view(np.int64), outs[1].view(np.int64))
+        post = _post(spec)
+        assert post.ctx.k1_variant is None
+        got = post.log_probability_batch(th).cpu().numpy()          # >= 2^15 rows: tunes on first use
+        assert post.ctx.k1_variant in (0, 1)
+        assert np.array_equal(got.view(np.int64), outs[0].view(np.int64))
+        assert np.array_equal(post.log_probability_batch(theta).view(np.int64), outs[0].view(np.int64))
+
+
 def test_full_size_c3_properties(cuda):
     """BASELINE config 3 at full size (1e6 x 1000 x 5): invariants + an oracle-checked subsample."""
     from oracle import oracle_c
