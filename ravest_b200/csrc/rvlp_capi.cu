@@ -91,7 +91,10 @@ int simple_grid(int64_t n) {
 // K1 shapes (rvlp_kernels.cuh: logprob_kernel<W, MB>); variant 0 is the default until rvlp_ctx_autotune ran
 typedef void (*k1_fn)(DevProblem, const double*, int64_t, double*, double*, double*, int, unsigned long long*);
 constexpr int kK1Variants = 2;
-static k1_fn k1_variant(int v) { return v == 1 ? logprob_kernel<2, 3> : logprob_kernel<kW, RVLP_MIN_BLOCKS>; }
+static k1_fn k1_variant(int v, bool ge) {
+  if (ge) return v == 1 ? logprob_kernel<2, 3, true> : logprob_kernel<kW, RVLP_MIN_BLOCKS, true>;
+  return v == 1 ? logprob_kernel<2, 3, false> : logprob_kernel<kW, RVLP_MIN_BLOCKS, false>;
+}
 
 constexpr int kTicketRing = 256;   // launches in flight per context before a counter is reused
 
@@ -200,7 +203,11 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
   P.priors = reinterpret_cast<const rvlp_prior*>(c->d_priors);
 
   CTX_TRY(cudaDeviceGetAttribute(&c->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  const SmemLayout L = smem_layout(P);
+  SmemLayout L = smem_layout(P);
+  if (L.total > c->max_smem && !P.n_hyper) {   // too many epochs to stage per CTA: leave them in global memory
+    P.epochs_global = 1;
+    L = smem_layout(P);
+  }
   c->smem_main = L.total;
   if (c->smem_main > c->max_smem) {
     int rc = fail(RVLP_EUNSUPPORTED, "problem needs %d B of shared memory per CTA (> %d): too many epochs",
@@ -209,7 +216,7 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
     return rc;
   }
   for (int v = 0; v < kK1Variants; ++v)
-    CTX_TRY(cudaFuncSetAttribute(k1_variant(v), cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CTX_TRY(cudaFuncSetAttribute(k1_variant(v, P.epochs_global != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   CTX_TRY(cudaFuncSetAttribute(rv_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   CTX_TRY(cudaFuncSetAttribute(walker_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   if (P.n_hyper) {
@@ -264,7 +271,7 @@ static int launch_logprob(rvlp_ctx* c, const double* theta, int64_t S, double* o
                           cudaStream_t st) {
   if (S == 0) return RVLP_OK;
   int grid = 0;
-  const k1_fn kern = k1_variant(c->k1);
+  const k1_fn kern = k1_variant(c->k1, c->P.epochs_global != 0);
   int rc = grid_for(c->device, (const void*)kern, c->smem_main, INT_MAX, &grid);   // full wave
   if (rc) return rc;
   // samples per prologue batch: kG when every resident warp still gets a batch, else 1 (latency of small S)

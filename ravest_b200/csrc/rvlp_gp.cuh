@@ -37,7 +37,7 @@ gp_logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, dou
   const SmemLayout L = smem_layout(P);
   const GpSmem G = gp_smem(P, L);
   stage_problem(P, L, smem);
-  const Tables T = tables_of(L, smem);
+  const Tables T = tables_of(P, L, smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
   double* scratch = reinterpret_cast<double*>(smem + L.off_scratch);   // warp 0's slot, sample g = 0
@@ -179,7 +179,7 @@ gp_logprob_tiled_kernel(DevProblem P, const double* __restrict__ theta, int64_t 
   const SmemLayout L = smem_layout(P);
   const GpTiledSmem G = gp_tiled_smem(P, L);
   stage_problem(P, L, smem);
-  const Tables T = tables_of(L, smem);
+  const Tables T = tables_of(P, L, smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
   double* scratch = reinterpret_cast<double*>(smem + L.off_scratch);
@@ -372,7 +372,7 @@ gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_
   const SmemLayout L = smem_layout(P);
   const GpBlockedSmem G = gp_blocked_smem(P, L, TT);
   stage_problem(P, L, smem);
-  const Tables T = tables_of(L, smem);
+  const Tables T = tables_of(P, L, smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
   double* scratch = reinterpret_cast<double*>(smem + L.off_scratch);
@@ -584,7 +584,7 @@ gp_predict_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, con
   const SmemLayout L = smem_layout(P);
   const GpPredictSmem G = gp_predict_smem(P, L);
   stage_problem(P, L, smem);
-  const Tables T = tables_of(L, smem);
+  const Tables T = tables_of(P, L, smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
   double* scratch = reinterpret_cast<double*>(smem + L.off_scratch);

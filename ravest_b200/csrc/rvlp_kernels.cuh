@@ -53,6 +53,7 @@ constexpr double kLog2Pi = 1.8378770664093453;   // np.log(2*np.pi), fit.py:3595
 // Device view of a context: descriptor tables + resident epoch arrays (all device pointers).
 struct DevProblem {
   int n_planets, par, n_inst, ndim, n_priors, n_hyper, n_model, n_epochs, n_pad;
+  int epochs_global;   // 1: too many epochs for shared memory - the kernels read them from global memory (L1 / L2)
   double t0, jacobian, renorm;
   const int32_t* src_col;
   const double* src_const;
@@ -77,10 +78,11 @@ struct SmemLayout {
 __host__ __device__ inline SmemLayout smem_layout(const DevProblem& P) {
   SmemLayout L;
   int o = 0;
-  L.off_t = o; o += P.n_pad * 8;
-  L.off_v = o; o += P.n_pad * 8;
-  L.off_e2 = o; o += P.n_pad * 8;
-  L.off_inst = o; o += P.n_pad * 4;
+  const int ns = P.epochs_global ? 0 : P.n_pad;           // epochs staged in shared memory
+  L.off_t = o; o += ns * 8;
+  L.off_v = o; o += ns * 8;
+  L.off_e2 = o; o += ns * 8;
+  L.off_inst = o; o += ns * 4;
   o = (o + 15) & ~15;
   L.off_priors = o; o += P.n_priors * (int)sizeof(rvlp_prior);
   L.off_srcconst = o; o += (P.n_model + P.n_hyper) * 8;
@@ -132,7 +134,7 @@ __device__ __forceinline__ void stage_problem(const DevProblem& P, const SmemLay
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && !P.epochs_global) {
     mbar_expect_tx(bar, epoch_bytes);
     bulk_g2s(smem + L.off_t, P.epochs, epoch_bytes, bar);
   }
@@ -150,7 +152,7 @@ __device__ __forceinline__ void stage_problem(const DevProblem& P, const SmemLay
       di[i] = P.src_col[i];
     }
   }
-  mbar_wait(bar, 0);
+  if (!P.epochs_global) mbar_wait(bar, 0);
   __syncthreads();
 }
 
@@ -181,12 +183,22 @@ struct Tables {
   const int* src_col;
 };
 
-__device__ __forceinline__ Tables tables_of(const SmemLayout& L, unsigned char* smem) {
+// GE (compile time): the epoch arrays stay in global memory (P.epochs_global) instead of shared memory; a
+// template parameter rather than a run-time select so that the common path keeps its LDS loads.
+template <bool GE = false>
+__device__ __forceinline__ Tables tables_of(const DevProblem& P, const SmemLayout& L, unsigned char* smem) {
   Tables T;
-  T.t = reinterpret_cast<const double*>(smem + L.off_t);
-  T.v = reinterpret_cast<const double*>(smem + L.off_v);
-  T.e2 = reinterpret_cast<const double*>(smem + L.off_e2);
-  T.inst = reinterpret_cast<const int*>(smem + L.off_inst);
+  if (GE) {
+    T.t = P.epochs;
+    T.v = P.epochs + P.n_pad;
+    T.e2 = P.epochs + 2 * (size_t)P.n_pad;
+    T.inst = reinterpret_cast<const int*>(P.epochs + 3 * (size_t)P.n_pad);
+  } else {
+    T.t = reinterpret_cast<const double*>(smem + L.off_t);
+    T.v = reinterpret_cast<const double*>(smem + L.off_v);
+    T.e2 = reinterpret_cast<const double*>(smem + L.off_e2);
+    T.inst = reinterpret_cast<const int*>(smem + L.off_inst);
+  }
   T.priors = reinterpret_cast<const rvlp_prior*>(smem + L.off_priors);
   T.src_const = reinterpret_cast<const double*>(smem + L.off_srcconst);
   T.src_col = reinterpret_cast<const int*>(smem + L.off_srccol);
@@ -458,7 +470,7 @@ __device__ __forceinline__ void sample_chi_pipelined(const DevProblem& P, const 
 // is 10 % ahead on the high-eccentricity config and 4 % on 120-epoch data); rvlp_ctx_autotune times both on
 // the caller's own rows.  A lane visits its epochs (lane, lane + 32, ...) in ascending order for either W, so
 // the choice never changes a bit of the result.
-template <int W, int MB>
+template <int W, int MB, bool GE>
 __global__ void __launch_bounds__(kThreads, MB)
 logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double* __restrict__ out,
                double* __restrict__ ll_out, double* __restrict__ lp_out, int nb,
@@ -466,7 +478,7 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = smem_layout(P);
   stage_problem(P, L, smem);
-  const Tables T = tables_of(L, smem);
+  const Tables T = tables_of<GE>(P, L, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
   double* scratch = reinterpret_cast<double*>(smem + L.off_scratch) + warp * kG * rec;
@@ -546,7 +558,7 @@ rv_matrix_kernel(DevProblem P, const double* __restrict__ theta, int64_t S,
   const SmemLayout L = smem_layout(P);
   stage_problem(P, L, smem);
   if (frozen.n) apply_frozen(frozen, L, smem);     // kernel-uniform
-  const Tables T = tables_of(L, smem);
+  const Tables T = tables_of(P, L, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
   double* scratch = reinterpret_cast<double*>(smem + L.off_scratch) + warp * kG * rec;
@@ -608,7 +620,7 @@ walker_check_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, i
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = smem_layout(P);
   stage_problem(P, L, smem);
-  const Tables T = tables_of(L, smem);
+  const Tables T = tables_of(P, L, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
   double* scratch = reinterpret_cast<double*>(smem + L.off_scratch) + warp * kG * rec;

@@ -466,10 +466,33 @@ def test_ragged_and_tiny_shapes(cuda):
         post.log_probability_batch(th[:, :-1])
 
 
-def test_too_many_epochs_is_a_clean_error(cuda):
+@pytest.mark.parametrize("N", [7000, 9000, 30000])
+def test_more_epochs_than_fit_in_shared_memory(cuda, N):
+    """Beyond ~7 500 epochs the arrays no longer fit a CTA's shared memory: the kernels then read them from
+    global memory (logprob_kernel<..., GE = true>).  Same results as the oracle, both kernel shapes, same bits."""
+    from oracle import oracle_c
+    from ravest_b200 import workloads
+    spec, theta = workloads.make_multiplanet(2, N, 96, seed=2, t_span=float(N), instruments=("A", "B"),
+                                             invalid_frac=0.05)
+    ref = oracle_c.OracleProblem(spec).logprob(theta)
+    outs = []
+    for v in (0, 1):
+        post = _post(spec)
+        post.ctx.set_variant(v)
+        outs.append(post.log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy())
+        assert_logp_close(outs[-1], ref, f"N={N} variant {v}")
+    assert np.array_equal(outs[0].view(np.int64), outs[1].view(np.int64))
+    post = _post(spec)
+    times = np.linspace(0.0, float(N), 300)
+    m = post.rv_total_from_samples(times, theta).cpu().numpy()
+    good = post.check_walker_positions(theta)[0]
+    assert np.isfinite(m[good]).all() and good.sum() > 50
+
+
+def test_gp_with_too_many_epochs_is_a_clean_error(cuda):
     from ravest_b200 import _lib, workloads
-    spec, theta = workloads.make_multiplanet(1, 9000, 4, seed=2, t_span=9000.0)
-    with pytest.raises(_lib.RvlpError):
+    spec, theta = workloads.make_c5(n_samples=4, n_planets=1, n_epochs=700)
+    with pytest.raises(_lib.RvlpError, match="shared memory"):
         _post(spec).log_probability_batch(theta)
 
 

@@ -190,6 +190,51 @@ def test_gp_restatement_self_consistent():
     assert abs(ll - pr.gp_log_likelihood(params, hyper)) < 1e-8 * max(1, abs(ll))
 
 
+def test_gp_restatement_against_50_digit_arithmetic():
+    """GP parity is unpinned against tinygp; what CAN be pinned is that the restated formula is evaluated
+    accurately: the same log-density and conditional mean in 50-digit mpmath arithmetic at N = 8."""
+    mp = pytest.importorskip("mpmath")
+    from ravest_b200 import workloads
+    mp.mp.dps = 50
+    spec, theta = workloads.make_c5(n_samples=12, seed=31, n_epochs=8)
+    pr = oracle_py.Problem(spec)
+    names = pr.free_names + pr.free_hyper
+    done = 0
+    for row in theta:
+        comb = dict(zip(names, map(float, row)))
+        if not np.isfinite(pr.gp_log_probability(comb)):
+            continue
+        params = pr.fixed | {k: comb[k] for k in pr.free_names}
+        hyper = pr.fixed_hyper | {k: comb[k] for k in pr.free_hyper}
+        A, le, lpp, Pg = (mp.mpf(hyper[k]) for k in ("gp_amp", "gp_lambda_e", "gp_lambda_p", "gp_period"))
+        t = [mp.mpf(float(x)) for x in pr.time]
+        n = len(t)
+
+        def k(a, b):
+            tau = a - b
+            return A ** 2 * mp.exp(-mp.sin(mp.pi * abs(tau) / Pg) ** 2 / (2 * lpp ** 2)) * mp.exp(-tau ** 2 / (2 * le ** 2))
+
+        jit = np.array([params[f"jit_{i}"] for i in pr.unique])[pr.inst_idx]
+        C = mp.matrix(n, n)
+        for i in range(n):
+            for j in range(n):
+                C[i, j] = k(t[i], t[j]) + (mp.mpf(float(pr.velerr[i])) ** 2 + mp.mpf(float(jit[i])) ** 2 if i == j else 0)
+        r = mp.matrix([mp.mpf(float(x)) for x in (pr.vel - pr.mean_model(params))])
+        x = mp.lu_solve(C, r)
+        ll = -(r.T * x)[0] / 2 - mp.log(mp.det(C)) / 2 - mp.mpf(n) / 2 * mp.log(2 * mp.pi)
+        assert abs(float(ll) - pr.gp_log_likelihood(params, hyper)) < 1e-10 * max(1.0, abs(float(ll)))
+        ts = np.linspace(pr.time.min() - 1, pr.time.max() + 1, 5)
+        mu, chi2 = pr.gp_predict(comb, ts)
+        gam = np.array([params[f"g_{i}"] for i in pr.unique])[pr.inst_idx]
+        assert np.allclose(pr.vel - pr.mean_model(params), (pr.vel - gam) - (pr.mean_model(params) - gam), atol=1e-12)
+        for a, m in zip(ts, mu):
+            ref = sum(k(mp.mpf(float(a)), t[j]) * x[j] for j in range(n))
+            assert abs(float(ref) - m) < 1e-9 * max(1.0, abs(float(ref)))
+        assert abs(float((r.T * x)[0]) - chi2) < 1e-9 * max(1.0, chi2)
+        done += 1
+    assert done >= 5
+
+
 def test_live_reference_if_present():
     """In the build container the oracle is also checked against the live reference on fresh inputs."""
     from oracle.ref_import import import_reference, reference_available
