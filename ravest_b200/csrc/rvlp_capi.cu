@@ -15,6 +15,7 @@
 #include "rvlp_bands.cuh"
 #include "rvlp_gp.cuh"
 #include "rvlp_kernels.cuh"
+#include "rvlp_ws.cuh"
 
 using namespace rvlp;
 
@@ -53,10 +54,10 @@ struct DeviceGuard {
   }
 };
 
-int grid_for(int device, const void* kernel, int smem_bytes, int64_t want_blocks, int* grid) {
+int grid_for(int device, const void* kernel, int smem_bytes, int64_t want_blocks, int* grid, int threads = kThreads) {
   int sms = 0, per_sm = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, smem_bytes));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem_bytes));
   if (per_sm < 1) return fail(RVLP_EUNSUPPORTED, "kernel does not fit on an SM (smem %d B)", smem_bytes);
   int64_t g = (int64_t)sms * per_sm;      // one full wave of resident CTAs, persistent loop inside
   if (want_blocks < g) g = want_blocks;
@@ -90,10 +91,37 @@ int simple_grid(int64_t n) {
 
 // K1 shapes (rvlp_kernels.cuh: logprob_kernel<W, MB>); variant 0 is the default until rvlp_ctx_autotune ran
 typedef void (*k1_fn)(DevProblem, const double*, int64_t, double*, double*, double*, int, unsigned long long*);
-constexpr int kK1Variants = 2;
-static k1_fn k1_variant(int v, bool ge) {
-  if (ge) return v == 1 ? logprob_kernel<2, 3, true> : logprob_kernel<kW, RVLP_MIN_BLOCKS, true>;
-  return v == 1 ? logprob_kernel<2, 3, false> : logprob_kernel<kW, RVLP_MIN_BLOCKS, false>;
+// 0: logprob_kernel<4, 2>   1: logprob_kernel<2, 3>
+// 2, 3: logprob_ws_kernel, 8 producers x 2 consumers each, 24 warps, 1 CTA/SM, setmaxnreg 40 / 96 and 32 / 104
+//       (the launch pool is 768 x 80 registers: 8 x 32 x RP + 16 x 32 x RC must not exceed it or the
+//        consumers' setmaxnreg.inc never returns)
+// 4: logprob_ws_kernel, 4 producers x 1 consumer, 8 warps, 2 CTAs/SM
+constexpr int kK1Variants = 5;
+struct K1Shape {
+  k1_fn fn;
+  int threads;
+  int workers;      // sample streams per CTA: warps, or (producer, consumer) links
+  int smem;         // dynamic shared memory
+  int max_nb;       // samples per prologue batch
+};
+static K1Shape k1_shape(int v, const DevProblem& P, const SmemLayout& L) {
+  const bool ge = P.epochs_global != 0;
+  K1Shape s{};
+  s.threads = kThreads;
+  s.workers = kWarps;
+  s.smem = L.total;
+  s.max_nb = kG;
+  switch (v) {
+    case 1: s.fn = ge ? logprob_kernel<2, 3, true> : logprob_kernel<2, 3, false>; break;
+    case 2: s.fn = ge ? logprob_ws_kernel<4, 8, 2, 1, 56, 88, true> : logprob_ws_kernel<4, 8, 2, 1, 56, 88, false>;
+            s.threads = 768; s.workers = 16; s.smem = ws_smem(P, L, 4, 8, 2).total; s.max_nb = kGws; break;
+    case 3: s.fn = ge ? logprob_ws_kernel<4, 8, 2, 1, 48, 96, true> : logprob_ws_kernel<4, 8, 2, 1, 48, 96, false>;
+            s.threads = 768; s.workers = 16; s.smem = ws_smem(P, L, 4, 8, 2).total; s.max_nb = kGws; break;
+    case 4: s.fn = ge ? logprob_ws_kernel<4, 4, 1, 2, 0, 0, true> : logprob_ws_kernel<4, 4, 1, 2, 0, 0, false>;
+            s.threads = 256; s.workers = 4; s.smem = ws_smem(P, L, 4, 4, 1).total; s.max_nb = kGws; break;
+    default: s.fn = ge ? logprob_kernel<kW, RVLP_MIN_BLOCKS, true> : logprob_kernel<kW, RVLP_MIN_BLOCKS, false>;
+  }
+  return s;
 }
 
 constexpr int kTicketRing = 256;   // launches in flight per context before a counter is reused
@@ -216,7 +244,7 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
     return rc;
   }
   for (int v = 0; v < kK1Variants; ++v)
-    CTX_TRY(cudaFuncSetAttribute(k1_variant(v, P.epochs_global != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CTX_TRY(cudaFuncSetAttribute(k1_shape(v, P, L).fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   CTX_TRY(cudaFuncSetAttribute(rv_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   CTX_TRY(cudaFuncSetAttribute(walker_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   if (P.n_hyper) {
@@ -271,20 +299,24 @@ static int launch_logprob(rvlp_ctx* c, const double* theta, int64_t S, double* o
                           cudaStream_t st) {
   if (S == 0) return RVLP_OK;
   int grid = 0;
-  const k1_fn kern = k1_variant(c->k1, c->P.epochs_global != 0);
-  int rc = grid_for(c->device, (const void*)kern, c->smem_main, INT_MAX, &grid);   // full wave
+  SmemLayout L = smem_layout(c->P);
+  K1Shape shape = k1_shape(c->k1, c->P, L);
+  if (shape.smem > c->max_smem) shape = k1_shape(0, c->P, L);   // rings do not fit next to this many epochs
+  const k1_fn kern = shape.fn;
+  const int smem = shape.smem;
+  int rc = grid_for(c->device, (const void*)kern, smem, INT_MAX, &grid, shape.threads);   // full wave
   if (rc) return rc;
-  // samples per prologue batch: kG when every resident warp still gets a batch, else 1 (latency of small S)
-  int64_t per_warp = S / ((int64_t)grid * kWarps);
-  const int nb = (int)(per_warp >= kG ? kG : (per_warp < 1 ? 1 : per_warp));
-  const int64_t want = ((S + nb - 1) / nb + kWarps - 1) / kWarps;
+  // samples per prologue batch: kG when every resident worker still gets a batch, else 1 (latency of small S)
+  int64_t per_warp = S / ((int64_t)grid * shape.workers);
+  const int nb = (int)(per_warp >= shape.max_nb ? shape.max_nb : (per_warp < 1 ? 1 : per_warp));
+  const int64_t want = ((S + nb - 1) / nb + shape.workers - 1) / shape.workers;
   if (want < grid) grid = (int)want;
   unsigned long long* tickets = nullptr;
   if (per_warp >= 2) {                                     // several batches per warp: dynamic schedule
     tickets = c->d_tickets + (c->ticket_slot.fetch_add(1) % kTicketRing);
     CUDA_TRY(cudaMemsetAsync(tickets, 0, sizeof(unsigned long long), st));
   }
-  kern<<<grid, kThreads, c->smem_main, st>>>(c->P, theta, S, out, ll, lp, nb, tickets);
+  kern<<<grid, shape.threads, smem, st>>>(c->P, theta, S, out, ll, lp, nb, tickets);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return RVLP_OK;

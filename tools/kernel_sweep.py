@@ -12,16 +12,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VDIR = os.path.join(ROOT, "build_variants")
 VARIANTS = {
-    "w4_mb2": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=2"],
-    "w4_mb2_pipe3": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=2", "-DRVLP_PIPELINE=3"],
-    "w4_mb2_pipe1": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=2", "-DRVLP_PIPELINE=1"],
-    "w3_mb2": ["-DRVLP_W=3", "-DRVLP_MIN_BLOCKS=2"],
-    "w2_mb3": ["-DRVLP_W=2", "-DRVLP_MIN_BLOCKS=3"],
-    "w2_mb4": ["-DRVLP_W=2", "-DRVLP_MIN_BLOCKS=4"],
-    "w6_mb1": ["-DRVLP_W=6", "-DRVLP_MIN_BLOCKS=1", "-DRVLP_WP=2"],
-    "w8_mb1": ["-DRVLP_W=8", "-DRVLP_MIN_BLOCKS=1", "-DRVLP_WP=2"],
-    "w4_mb2_t128": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=4", "-DRVLP_THREADS=128"],
-    "w4_mb1_t512": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=1", "-DRVLP_THREADS=512"],
+    "full": [],
+    "skipA": ["-DRVLP_EXP_SKIP_A"],
+    "skipB": ["-DRVLP_EXP_SKIP_B"],
+    "skipAB": ["-DRVLP_EXP_SKIP_A", "-DRVLP_EXP_SKIP_B"],
 }
 
 CHILD = r"""
