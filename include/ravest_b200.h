@@ -129,8 +129,7 @@ int rvlp_logprob_batch(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples
  * speed only - every shape produces identical bits (tests/test_gpu_parity.py). */
 int rvlp_ctx_autotune(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples, int32_t* chosen);
 
-/* Diagnostic: force shape `variant` (0..3: warp-per-sample W=4 / W=2, warp-specialised W=4 / W=2) of the
- * log-probability kernel for this context. */
+/* Diagnostic: force shape `variant` (0 or 1) of the log-probability kernel for this context. */
 int rvlp_ctx_set_variant(rvlp_ctx* ctx, int32_t variant);
 
 /* Same call for HOST buffers (what a NumPy caller such as emcee holds): pinned staging,

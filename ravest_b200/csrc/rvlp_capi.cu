@@ -15,7 +15,6 @@
 #include "rvlp_bands.cuh"
 #include "rvlp_gp.cuh"
 #include "rvlp_kernels.cuh"
-#include "rvlp_ws.cuh"
 
 using namespace rvlp;
 
@@ -92,15 +91,11 @@ int simple_grid(int64_t n) {
 // K1 shapes (rvlp_kernels.cuh: logprob_kernel<W, MB>); variant 0 is the default until rvlp_ctx_autotune ran
 typedef void (*k1_fn)(DevProblem, const double*, int64_t, double*, double*, double*, int, unsigned long long*);
 // 0: logprob_kernel<4, 2>   1: logprob_kernel<2, 3>
-// 2, 3: logprob_ws_kernel, 8 producers x 2 consumers each, 24 warps, 1 CTA/SM, setmaxnreg 40 / 96 and 32 / 104
-//       (the launch pool is 768 x 80 registers: 8 x 32 x RP + 16 x 32 x RC must not exceed it or the
-//        consumers' setmaxnreg.inc never returns)
-// 4: logprob_ws_kernel, 4 producers x 1 consumer, 8 warps, 2 CTAs/SM
-constexpr int kK1Variants = 5;
+constexpr int kK1Variants = 2;
 struct K1Shape {
   k1_fn fn;
   int threads;
-  int workers;      // sample streams per CTA: warps, or (producer, consumer) links
+  int workers;      // sample streams per CTA (warps)
   int smem;         // dynamic shared memory
   int max_nb;       // samples per prologue batch
 };
@@ -111,16 +106,8 @@ static K1Shape k1_shape(int v, const DevProblem& P, const SmemLayout& L) {
   s.workers = kWarps;
   s.smem = L.total;
   s.max_nb = kG;
-  switch (v) {
-    case 1: s.fn = ge ? logprob_kernel<2, 3, true> : logprob_kernel<2, 3, false>; break;
-    case 2: s.fn = ge ? logprob_ws_kernel<4, 8, 2, 1, 56, 88, true> : logprob_ws_kernel<4, 8, 2, 1, 56, 88, false>;
-            s.threads = 768; s.workers = 16; s.smem = ws_smem(P, L, 4, 8, 2).total; s.max_nb = kGws; break;
-    case 3: s.fn = ge ? logprob_ws_kernel<4, 8, 2, 1, 48, 96, true> : logprob_ws_kernel<4, 8, 2, 1, 48, 96, false>;
-            s.threads = 768; s.workers = 16; s.smem = ws_smem(P, L, 4, 8, 2).total; s.max_nb = kGws; break;
-    case 4: s.fn = ge ? logprob_ws_kernel<4, 4, 1, 2, 0, 0, true> : logprob_ws_kernel<4, 4, 1, 2, 0, 0, false>;
-            s.threads = 256; s.workers = 4; s.smem = ws_smem(P, L, 4, 4, 1).total; s.max_nb = kGws; break;
-    default: s.fn = ge ? logprob_kernel<kW, RVLP_MIN_BLOCKS, true> : logprob_kernel<kW, RVLP_MIN_BLOCKS, false>;
-  }
+  if (v == 1) s.fn = ge ? logprob_kernel<2, 3, true> : logprob_kernel<2, 3, false>;
+  else s.fn = ge ? logprob_kernel<kW, RVLP_MIN_BLOCKS, true> : logprob_kernel<kW, RVLP_MIN_BLOCKS, false>;
   return s;
 }
 

@@ -17,11 +17,7 @@
 
 #if defined(__CUDACC__)
 #define RV_HD __host__ __device__ __forceinline__
-#if defined(RVLP_INLINE_SLOW)
-#define RV_SLOW __host__ __device__ inline
-#else
 #define RV_SLOW __host__ __device__ __noinline__
-#endif
 #else
 #define RV_HD inline
 #define RV_SLOW inline
@@ -631,53 +627,6 @@ RV_HD void planet_rv_add(const PlanetConst& pc, const SolverPlan& plan, const do
 #pragma unroll
   for (int i = 0; i < W; ++i) {
     // model.py:119-121, 170 with K, cos w, sin w folded into A, B, C (C == e A)
-    const double u = ffma(-sE[i], pc.B, ffma(cE[i], pc.A, -pc.C));
-    rv[i] = ffma(ri[i], u, rv[i]);
-  }
-}
-
-// The two halves of planet_rv_add for the warp-specialised kernel (rvlp_ws.cuh): a producer warp runs stage A,
-// a consumer warp stage B + the RV sum.  Same operations on the same values as planet_rv_add, so the same bits.
-// Only called for e != 0 (the circular branch has no stage A; the consumer handles it through planet_rv_add).
-template <int W>
-RV_HD void planet_starter(const PlanetConst& pc, const SolverPlan& plan, const double (&t)[W], StarterOut<W>& o) {
-  double M[W];
-#pragma unroll
-  for (int i = 0; i < W; ++i) M[i] = mean_anomaly(pc.n, t[i], pc.tp);
-  if (plan.n32 == 1) kepler_stage_a<W, 1>(M, pc.e, 1, o);
-  else if (plan.n32 == 2) kepler_stage_a<W, 2>(M, pc.e, 2, o);
-  else kepler_stage_a<W>(M, pc.e, plan.n32, o);
-  // |M| too large for the Cody-Waite reduction: poison m so that the consumer's step test rejects the lane
-  // (NaN step) and sends it through kepler_robust, exactly the lanes planet_rv_add sends there
-#pragma unroll
-  for (int i = 0; i < W; ++i)
-    if (anomaly_is_big(M[i])) o.m[i] = NAN;
-}
-
-template <int W>
-RV_HD void planet_rv_from_starter(const PlanetConst& pc, const SolverPlan& plan, const double (&t)[W],
-                                  const StarterOut<W>& o, double (&rv)[W]) {
-  double cE[W], sE[W], dl[W], ri[W];
-  if (plan.n64 == 0) kepler_stage_b<W, 0>(o, pc.e, 0, cE, sE, dl, ri);
-  else if (plan.n64 == 1) kepler_stage_b<W, 1>(o, pc.e, 1, cE, sE, dl, ri);
-  else kepler_stage_b<W>(o, pc.e, plan.n64, cE, sE, dl, ri);
-  bool bad = false;
-#pragma unroll
-  for (int i = 0; i < W; ++i) bad |= step_rejected(dl[i], plan.tol);
-  if (RV_ANY(bad)) {                        // warp-uniform branch; rare
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-      const double Mi = mean_anomaly(pc.n, t[i], pc.tp);
-      if (step_rejected(dl[i], plan.tol) || anomaly_is_big(Mi)) {
-        const CosSin cs = kepler_robust(Mi, pc.e);
-        cE[i] = cs.c;
-        sE[i] = cs.s;
-        ri[i] = 1.0 / (1.0 - pc.e * cs.c);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < W; ++i) {
     const double u = ffma(-sE[i], pc.B, ffma(cE[i], pc.A, -pc.C));
     rv[i] = ffma(ri[i], u, rv[i]);
   }
