@@ -17,6 +17,20 @@
 namespace rvlp {
 
 __host__ __device__ inline int gp_tri_doubles(int N) { return (N + 1) * (N + 2) / 2; }
+
+// 1 / sqrt(x) for the pivots of the diagonal-tile factorisation, which sits on K3's critical path (one thread
+// works, the CTA waits): MUFU.RSQ64H seed (~2^-20) + two Newton-Raphson steps (-> 2^-40 -> full precision) instead
+// of libm's rsqrt.  Negative / zero / NaN pivots (matrix not positive definite) still give NaN / inf, as jax.
+__device__ __forceinline__ double pivot_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double hx = 0.5 * x;
+  double e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-hx * y, y, 0.5);
+  y = fma(y, e, y);
+  return y;
+}
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
 struct GpSmem {
@@ -457,7 +471,7 @@ gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_
         for (int c = 0; c < TT; ++c) {
           const bool valid = c0 + c < N;                       // columns >= N: identity (no-op) column
           const double d = a[c][c];
-          const double inv = valid ? rsqrt(d) : 1.0;           // NaN when not positive definite (as jax)
+          const double inv = valid ? pivot_rsqrt(d) : 1.0;     // NaN when not positive definite (as jax)
           invd[c] = inv;
           a[c][c] = valid ? d * inv : 1.0;
           if (valid) {

@@ -12,10 +12,12 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VDIR = os.path.join(ROOT, "build_variants")
 VARIANTS = {
-    "full": [],
-    "skipA": ["-DRVLP_EXP_SKIP_A"],
-    "skipB": ["-DRVLP_EXP_SKIP_B"],
-    "skipAB": ["-DRVLP_EXP_SKIP_A", "-DRVLP_EXP_SKIP_B"],
+    "w4_mb2": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=2"],
+    "w4_t128_mb5": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=5", "-DRVLP_THREADS=128"],
+    "w3_mb3": ["-DRVLP_W=3", "-DRVLP_MIN_BLOCKS=3"],
+    "w3_t128_mb5": ["-DRVLP_W=3", "-DRVLP_MIN_BLOCKS=5", "-DRVLP_THREADS=128"],
+    "w5_mb2": ["-DRVLP_W=5", "-DRVLP_MIN_BLOCKS=2"],
+    "w5_t128_mb3": ["-DRVLP_W=5", "-DRVLP_MIN_BLOCKS=3", "-DRVLP_THREADS=128"],
 }
 
 CHILD = r"""
