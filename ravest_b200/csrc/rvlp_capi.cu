@@ -501,6 +501,7 @@ int rvlp_gp_logprob_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
   const bool use_smem = which && !strcmp(which, "smem");
   // measured on B200 (tools/gp_time.py): the panel kernel wins at T = 2 and 6, the column sweep at T = 4 and 8
   bool use_column = c->gp_tile == 4 || c->gp_tile == 8;
+  const char* grid_cap = getenv("RVLP_GP_GRID");          // experiments: cap the grid (e.g. 148 = one CTA per SM)
   if (which && !strcmp(which, "column")) use_column = true;
   if (which && !strcmp(which, "blocked")) use_column = false;
 #define RVLP_GP_TILED(TT)                                                                                   \
@@ -512,6 +513,7 @@ int rvlp_gp_logprob_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
     } else {                                                                                                \
       rc = grid_for(c->device, (const void*)gp_logprob_blocked_kernel<TT>, c->smem_gp_blocked, S, &grid);   \
       if (rc) return rc;                                                                                    \
+      if (grid_cap && atoi(grid_cap) > 0 && atoi(grid_cap) < grid) grid = atoi(grid_cap);                   \
       gp_logprob_blocked_kernel<TT><<<grid, kThreads, c->smem_gp_blocked, st>>>(c->P, theta_dev, S, out_dev); \
     }                                                                                                       \
     break;
@@ -530,6 +532,17 @@ int rvlp_gp_logprob_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
   CUDA_TRY(cudaGetLastError());
   return RVLP_OK;
 }
+
+#ifdef RVLP_GP_TIMING
+// experiments only (tools/gp_phase_time.py): read and clear the phase counters of the blocked GP kernel
+int rvlp_debug_gp_timing(unsigned long long* out32) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyFromSymbol(out32, g_gp_timing, 32 * sizeof(unsigned long long)));
+  unsigned long long z[32] = {0};
+  CUDA_TRY(cudaMemcpyToSymbol(g_gp_timing, z, sizeof(z)));
+  return RVLP_OK;
+}
+#endif
 
 int rvlp_gp_predict_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const double* times_dev, int64_t T,
                           double* mean_dev, double* chi2_dev, void* stream) {

@@ -13,6 +13,7 @@
 // the trailing update spread over the CTA.  fp64 throughout.
 #pragma once
 #include "rvlp_kernels.cuh"
+#include "rvlp_gpcov.cuh"
 
 namespace rvlp {
 
@@ -83,8 +84,7 @@ gp_logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, dou
     const double* row = theta + s * P.ndim;
     const double A = model_param(T, row, P.n_model + 0), le = model_param(T, row, P.n_model + 1);
     const double lpp = model_param(T, row, P.n_model + 2), Pg = model_param(T, row, P.n_model + 3);
-    const double gamma = 1.0 / (2.0 * (lpp * lpp));          // gp.py:152
-    const double A2 = A * A, inv_le = 1.0 / le, inv_Pg = 1.0 / Pg;
+    const GpHyper hyp = gp_hyper(A, le, lpp, Pg);            // gp.py:145-156
 
     // residual row (index N): v - (planets + trend + gamma_inst)   fit.py:7994-8043, 8059
     int nonfinite = 0;
@@ -102,10 +102,7 @@ gp_logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, dou
       while (tri(i + 1, 0) <= p) ++i;
       while (tri(i, 0) > p) --i;
       const int j = p - tri(i, 0);
-      const double tau = T.t[i] - T.t[j];
-      const double sn = sinpi(fabs(tau) * inv_Pg);
-      const double q = tau * inv_le;
-      double c = A2 * exp(-gamma * (sn * sn)) * exp(-0.5 * (q * q));
+      double c = gp_cov(T.t[i] - T.t[j], hyp);
       if (i == j) c += T.e2[i] + sr[kHdr + P.n_inst + T.inst[i]];
       Cm[p] = c;
     }
@@ -244,8 +241,7 @@ gp_logprob_tiled_kernel(DevProblem P, const double* __restrict__ theta, int64_t 
     const double* row = theta + s * P.ndim;
     const double Aamp = model_param(T, row, P.n_model + 0), le = model_param(T, row, P.n_model + 1);
     const double lpp = model_param(T, row, P.n_model + 2), Pg = model_param(T, row, P.n_model + 3);
-    const double gamma = 1.0 / (2.0 * (lpp * lpp));          // gp.py:152
-    const double A2 = Aamp * Aamp, inv_le = 1.0 / le, inv_Pg = 1.0 / Pg;
+    const GpHyper hyp = gp_hyper(Aamp, le, lpp, Pg);         // gp.py:145-156
 
     // build this thread's tile                               gp.py:145-156, fit.py:8094-8096
     double a[TT][TT];
@@ -259,14 +255,15 @@ gp_logprob_tiled_kernel(DevProblem P, const double* __restrict__ theta, int64_t 
 #ifdef RVLP_GP_SKIP_BUILD
         if (has_tile && i < N && k <= i) { v = (i == k) ? 10.0 + i : 0.001; } else
 #endif
-        if (has_tile && i < N && k <= i) {
-          const double tau = T.t[i] - T.t[k];
-          const double sn = sinpi(fabs(tau) * inv_Pg);
-          const double q = tau * inv_le;
-          v = A2 * exp(-gamma * (sn * sn) - 0.5 * (q * q));
-          if (i == k) v += T.e2[i] + sr[kHdr + P.n_inst + T.inst[i]];
-        } else if (has_tile && i == N && k < N) {
-          v = resid[k];
+        {
+          // branch-free (rvlp_gpcov.cuh): every element is evaluated, out-of-triangle ones are discarded, so
+          // the compiler interleaves the TT*TT independent chains instead of running them one after the other
+          const int ic = i < N ? i : N - 1, kc = k < N ? k : N - 1;
+          const double kv = gp_cov(T.t[ic] - T.t[kc], hyp);
+          const bool in_tri = has_tile && i < N && k <= i;
+          v = in_tri ? kv : 0.0;
+          if (in_tri && i == k) v += T.e2[i] + sr[kHdr + P.n_inst + T.inst[i]];
+          if (has_tile && i == N && k < N) v = resid[k];
         }
         a[r][c] = v;
       }
@@ -379,6 +376,18 @@ __host__ __device__ inline GpBlockedSmem gp_blocked_smem(const DevProblem& P, co
   return G;
 }
 
+#ifdef RVLP_GP_TIMING
+// Phase timing of the blocked kernel (experiments only; tools/gp_phase_time.py): block 0, thread of the last tile.
+__device__ unsigned long long g_gp_timing[32];
+#define GPT_DECL unsigned long long gpt[16] = {0}; long long gpt_t = 0; const bool gpt_on = blockIdx.x == 0 && tid == nt * (nt + 1) / 2 - 1;
+#define GPT_START() do { if (gpt_on) gpt_t = clock64(); } while (0)
+#define GPT_LAP(k) do { if (gpt_on) { const long long n_ = clock64(); gpt[k] += n_ - gpt_t; gpt_t = n_; } } while (0)
+#else
+#define GPT_DECL
+#define GPT_START() do {} while (0)
+#define GPT_LAP(k) do {} while (0)
+#endif
+
 template <int TT>
 __global__ void __launch_bounds__(kThreads, (TT >= 8 ? 1 : 2))
 gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double* __restrict__ out) {
@@ -403,10 +412,13 @@ gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_
   const bool has_tile = J < nt;
   const int r0 = I * TT, c0 = J * TT;
   const int IN = N / TT, rN = N - IN * TT;       // where the residual row lives
+  GPT_DECL
 
   for (int64_t s = blockIdx.x; s < S; s += gridDim.x) {
+    GPT_START();
     if (warp == 0) sample_prologue(P, T, theta, s, s + 1, scratch, rec, lane, true, 1);
     __syncthreads();
+    GPT_LAP(0);
     const double* sr = scratch;
     const int flags = __double2loint(sr[1]);
     const double lp = sr[0], lhp = sr[4];
@@ -435,11 +447,11 @@ gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_
       __syncthreads();
       continue;
     }
+    GPT_LAP(1);
     const double* row = theta + s * P.ndim;
     const double Aamp = model_param(T, row, P.n_model + 0), le = model_param(T, row, P.n_model + 1);
     const double lpp = model_param(T, row, P.n_model + 2), Pg = model_param(T, row, P.n_model + 3);
-    const double gamma = 1.0 / (2.0 * (lpp * lpp));          // gp.py:152
-    const double A2 = Aamp * Aamp, inv_le = 1.0 / le, inv_Pg = 1.0 / Pg;
+    const GpHyper hyp = gp_hyper(Aamp, le, lpp, Pg);         // gp.py:145-156
 
     double a[TT][TT];                                         // gp.py:145-156, fit.py:8094-8096
 #pragma unroll
@@ -449,23 +461,28 @@ gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_
       for (int c = 0; c < TT; ++c) {
         const int k = c0 + c;
         double v = 0.0;
-        if (has_tile && i < N && k <= i) {
-          const double tau = T.t[i] - T.t[k];
-          const double sn = sinpi(fabs(tau) * inv_Pg);
-          const double q = tau * inv_le;
-          v = A2 * exp(-gamma * (sn * sn) - 0.5 * (q * q));
-          if (i == k) v += T.e2[i] + sr[kHdr + P.n_inst + T.inst[i]];
-        } else if (has_tile && i == N && k < N) {
-          v = resid[k];
+        {
+          // branch-free (rvlp_gpcov.cuh): every element is evaluated, out-of-triangle ones are discarded, so
+          // the compiler interleaves the TT*TT independent chains instead of running them one after the other
+          const int ic = i < N ? i : N - 1, kc = k < N ? k : N - 1;
+          const double kv = gp_cov(T.t[ic] - T.t[kc], hyp);
+          const bool in_tri = has_tile && i < N && k <= i;
+          v = in_tri ? kv : 0.0;
+          if (in_tri && i == k) v += T.e2[i] + sr[kHdr + P.n_inst + T.inst[i]];
+          if (has_tile && i == N && k < N) v = resid[k];
         }
         a[r][c] = v;
       }
     }
     double quad = 0.0, prodm = 1.0;      // partial alpha.alpha and pivot product of THIS thread
     int exsum = 0;
+    GPT_LAP(2);
     for (int Jt = 0; Jt < ntc; ++Jt) {
       // ---- 1. diagonal tile: unblocked Cholesky in registers
       if (has_tile && I == Jt && J == Jt) {
+#ifdef RVLP_GP_TIMING
+        const long long d0_ = clock64();
+#endif
         double invd[TT];
 #pragma unroll
         for (int c = 0; c < TT; ++c) {
@@ -505,10 +522,17 @@ gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_
           for (int c = 0; c < TT; ++c) dbuf[r * TT + c] = (c <= r) ? a[r][c] : 0.0;
 #pragma unroll
         for (int c = 0; c < TT; ++c) dbuf[TT * TT + c] = invd[c];
+#ifdef RVLP_GP_TIMING
+        if (blockIdx.x == 0) atomicAdd(&g_gp_timing[9], (unsigned long long)(clock64() - d0_));
+#endif
       }
       __syncthreads();
+      GPT_LAP(Jt == 0 ? 3 : 4);
       // ---- 2. panel tiles: X L_d^T = A, publish X k-major
       if (has_tile && J == Jt && I > Jt) {
+#ifdef RVLP_GP_TIMING
+        const long long d0_ = clock64();
+#endif
 #pragma unroll
         for (int c = 0; c < TT; ++c) {
           const double inv = dbuf[TT * TT + c];
@@ -533,8 +557,12 @@ gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_
         for (int k = 0; k < TT; ++k)
 #pragma unroll
           for (int r = 0; r < TT; ++r) pb[k * TT + r] = a[r][k];
+#ifdef RVLP_GP_TIMING
+        if (blockIdx.x == 0 && I == Jt + 1) atomicAdd(&g_gp_timing[10], (unsigned long long)(clock64() - d0_));
+#endif
       }
       __syncthreads();
+      GPT_LAP(5);
       // ---- 3. trailing tiles: a -= P_I P_J^T
       if (has_tile && J > Jt) {
         const double2* pi = reinterpret_cast<const double2*>(pbuf + I * TT * TT);
@@ -554,6 +582,7 @@ gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_
             for (int c = 0; c < TT; ++c) a[r][c] = fma(-Li[r], Lk[c], a[r][c]);
         }
       }
+      GPT_LAP(6);
     }
     // fixed-order reduction of the per-thread partials (only a few threads hold non-trivial ones)
     red[tid] = quad;
@@ -569,7 +598,15 @@ gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_
       out[s] = r;
     }
     __syncthreads();
+    GPT_LAP(7);
+#ifdef RVLP_GP_TIMING
+    if (gpt_on) gpt[8] += 1;
+#endif
   }
+#ifdef RVLP_GP_TIMING
+  if (gpt_on)
+    for (int k = 0; k < 16; ++k) atomicAdd(&g_gp_timing[k], gpt[k]);
+#endif
 }
 
 // ------------------------------------------------------------------ K7: GP conditioning (row f-4)
@@ -618,8 +655,7 @@ gp_predict_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, con
     const double* row = theta + s * P.ndim;
     const double A = model_param(T, row, P.n_model + 0), le = model_param(T, row, P.n_model + 1);
     const double lpp = model_param(T, row, P.n_model + 2), Pg = model_param(T, row, P.n_model + 3);
-    const double gamma = 1.0 / (2.0 * (lpp * lpp));          // gp.py:152
-    const double A2 = A * A, inv_le = 1.0 / le, inv_Pg = 1.0 / Pg;
+    const GpHyper hyp = gp_hyper(A, le, lpp, Pg);            // gp.py:145-156
     if (!bad) {
       for (int i = tid; i < N; i += kThreads) {              // fit.py:6375-6380, 7536-7550
         double tt[1] = {T.t[i]}, rv[1];
@@ -632,10 +668,7 @@ gp_predict_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, con
         while (tri(i + 1, 0) <= p) ++i;
         while (tri(i, 0) > p) --i;
         const int j = p - tri(i, 0);
-        const double tau = T.t[i] - T.t[j];
-        const double sn = sinpi(fabs(tau) * inv_Pg);
-        const double q = tau * inv_le;
-        double c = A2 * exp(-gamma * (sn * sn) - 0.5 * (q * q));
+        double c = gp_cov(T.t[i] - T.t[j], hyp);
         if (i == j) c += T.e2[i] + sr[kHdr + P.n_inst + T.inst[i]];
         Cm[p] = c;
       }
@@ -694,12 +727,8 @@ gp_predict_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, con
     for (int64_t i = tid; i < T_n; i += kThreads) {
       const double ts = times[i];
       double acc = 0.0;
-      for (int j = 0; j < N; ++j) {
-        const double tau = ts - T.t[j];
-        const double sn = sinpi(fabs(tau) * inv_Pg);
-        const double qq = tau * inv_le;
-        acc = fma(A2 * exp(-gamma * (sn * sn) - 0.5 * (qq * qq)), beta[j], acc);
-      }
+#pragma unroll 4
+      for (int j = 0; j < N; ++j) acc = fma(gp_cov(ts - T.t[j], hyp), beta[j], acc);
       mean_out[s * T_n + i] = acc;
     }
     __syncthreads();

@@ -131,6 +131,17 @@ def test_host_compiled_solver_converges(mufu):
             assert fb == 0.0, ln          # the safety net is never needed where the fast plans apply
 
 
+def test_host_compiled_gp_covariance_is_accurate():
+    """The branch-free quasi-periodic covariance (rvlp_gpcov.cuh compiled for the host, contraction off so the
+    algorithm is tested as written) against a long-double evaluation of gp.py:145-156, plus edge inputs."""
+    exe = "/tmp/rvlp_gpcov_check"
+    src = os.path.join(ROOT, "tests", "host", "gpcov_check.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-mfma", "-ffp-contract=off", "-o", exe, src, "-lm"], check=True)
+    res = subprocess.run([exe, "400000"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout
+    assert res.stdout.strip().endswith("OK"), res.stdout
+
+
 def test_shard_bounds_cover_and_align():
     for S in (0, 1, 3, 4, 5, 31, 32, 1000, 100_003):
         for world in (1, 2, 3, 4, 8):
