@@ -14,6 +14,7 @@
 
 #include "rvlp_bands.cuh"
 #include "rvlp_gp.cuh"
+#include "rvlp_gp_pipe.cuh"
 #include "rvlp_kernels.cuh"
 
 using namespace rvlp;
@@ -120,7 +121,7 @@ struct rvlp_ctx {
   void* d_src_const = nullptr;
   void* d_priors = nullptr;
   void* d_epochs = nullptr;
-  int smem_main = 0, smem_gp = 0, smem_gp_tiled = 0, smem_gp_blocked = 0, gp_tile = 0, smem_gp_predict = 0;
+  int smem_main = 0, smem_gp = 0, smem_gp_tiled = 0, smem_gp_blocked = 0, smem_gp_pipe = 0, gp_tile = 0, smem_gp_predict = 0;
   int max_smem = 0;
   int k1 = 0;          // K1 variant in use
   int k1_tuned = 0;    // rvlp_ctx_autotune has run
@@ -248,6 +249,11 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
     c->gp_tile = gp_tile_for(P.n_epochs);
     c->smem_gp_tiled = gp_tiled_smem(P, L).total;
     c->smem_gp_blocked = c->gp_tile ? gp_blocked_smem(P, L, c->gp_tile).total : 0;
+    c->smem_gp_pipe = c->gp_tile ? gp_pipe_smem(P, L, c->gp_tile).total : 0;
+    CTX_TRY(cudaFuncSetAttribute(gp_logprob_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CTX_TRY(cudaFuncSetAttribute(gp_logprob_pipe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CTX_TRY(cudaFuncSetAttribute(gp_logprob_pipe_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CTX_TRY(cudaFuncSetAttribute(gp_logprob_pipe_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_blocked_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
@@ -496,17 +502,21 @@ int rvlp_gp_logprob_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
   int grid = 0;
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  // RVLP_GP_KERNEL=smem|column selects the older kernels (kept for cross-checks in the tests)
+  // The software-pipelined register-tile kernel (rvlp_gp_pipe.cuh) is the product path for N <= 175 epochs.
+  // RVLP_GP_KERNEL=smem|column|blocked selects the older lock-step kernels (kept for cross-checks in the tests).
   const char* which = getenv("RVLP_GP_KERNEL");
   const bool use_smem = which && !strcmp(which, "smem");
-  // measured on B200 (tools/gp_time.py): the panel kernel wins at T = 2 and 6, the column sweep at T = 4 and 8
-  bool use_column = c->gp_tile == 4 || c->gp_tile == 8;
-  const char* grid_cap = getenv("RVLP_GP_GRID");          // experiments: cap the grid (e.g. 148 = one CTA per SM)
+  bool use_column = false, use_pipe = !(which && *which) || !strcmp(which, "pipe");
   if (which && !strcmp(which, "column")) use_column = true;
-  if (which && !strcmp(which, "blocked")) use_column = false;
+  const char* grid_cap = getenv("RVLP_GP_GRID");          // experiments: cap the grid (e.g. 148 = one CTA per SM)
 #define RVLP_GP_TILED(TT)                                                                                   \
   case TT:                                                                                                  \
-    if (use_column) {                                                                                       \
+    if (use_pipe) {                                                                                         \
+      rc = grid_for(c->device, (const void*)gp_logprob_pipe_kernel<TT>, c->smem_gp_pipe, S, &grid);         \
+      if (rc) return rc;                                                                                    \
+      if (grid_cap && atoi(grid_cap) > 0 && atoi(grid_cap) < grid) grid = atoi(grid_cap);                   \
+      gp_logprob_pipe_kernel<TT><<<grid, kThreads, c->smem_gp_pipe, st>>>(c->P, theta_dev, S, out_dev);     \
+    } else if (use_column) {                                                                                \
       rc = grid_for(c->device, (const void*)gp_logprob_tiled_kernel<TT>, c->smem_gp_tiled, S, &grid);       \
       if (rc) return rc;                                                                                    \
       gp_logprob_tiled_kernel<TT><<<grid, kThreads, c->smem_gp_tiled, st>>>(c->P, theta_dev, S, out_dev);   \
@@ -540,6 +550,13 @@ int rvlp_debug_gp_timing(unsigned long long* out32) {
   CUDA_TRY(cudaMemcpyFromSymbol(out32, g_gp_timing, 32 * sizeof(unsigned long long)));
   unsigned long long z[32] = {0};
   CUDA_TRY(cudaMemcpyToSymbol(g_gp_timing, z, sizeof(z)));
+  return RVLP_OK;
+}
+int rvlp_debug_gp_pipe_timing(unsigned long long* out64) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyFromSymbol(out64, g_gp_pipe_timing, 64 * sizeof(unsigned long long)));
+  unsigned long long z[64] = {0};
+  CUDA_TRY(cudaMemcpyToSymbol(g_gp_pipe_timing, z, sizeof(z)));
   return RVLP_OK;
 }
 #endif

@@ -379,13 +379,28 @@ __host__ __device__ inline GpBlockedSmem gp_blocked_smem(const DevProblem& P, co
 #ifdef RVLP_GP_TIMING
 // Phase timing of the blocked kernel (experiments only; tools/gp_phase_time.py): block 0, thread of the last tile.
 __device__ unsigned long long g_gp_timing[32];
+#ifndef RVLP_GP_TIMING_SEL
+#define RVLP_GP_TIMING_SEL -1   /* -1: all phases (spills: indicative only); k: phase k alone, 4 registers */
+#endif
+#if RVLP_GP_TIMING_SEL < 0
 #define GPT_DECL unsigned long long gpt[16] = {0}; long long gpt_t = 0; const bool gpt_on = blockIdx.x == 0 && tid == nt * (nt + 1) / 2 - 1;
 #define GPT_START() do { if (gpt_on) gpt_t = clock64(); } while (0)
 #define GPT_LAP(k) do { if (gpt_on) { const long long n_ = clock64(); gpt[k] += n_ - gpt_t; gpt_t = n_; } } while (0)
+#define GPT_COUNT() do { if (gpt_on) gpt[8] += 1; } while (0)
+#define GPT_FLUSH() do { if (gpt_on) for (int k = 0; k < 16; ++k) atomicAdd(&g_gp_timing[k], gpt[k]); } while (0)
+#else
+#define GPT_DECL unsigned long long gpt_acc = 0, gpt_n = 0; long long gpt_t = 0; const bool gpt_on = blockIdx.x == 0 && tid == nt * (nt + 1) / 2 - 1;
+#define GPT_START() do { gpt_t = clock64(); } while (0)
+#define GPT_LAP(k) do { const long long n_ = clock64(); if ((k) == RVLP_GP_TIMING_SEL) gpt_acc += n_ - gpt_t; gpt_t = n_; } while (0)
+#define GPT_COUNT() do { gpt_n += 1; } while (0)
+#define GPT_FLUSH() do { if (gpt_on) { atomicAdd(&g_gp_timing[RVLP_GP_TIMING_SEL], gpt_acc); atomicAdd(&g_gp_timing[8], gpt_n); } } while (0)
+#endif
 #else
 #define GPT_DECL
 #define GPT_START() do {} while (0)
 #define GPT_LAP(k) do {} while (0)
+#define GPT_COUNT() do {} while (0)
+#define GPT_FLUSH() do {} while (0)
 #endif
 
 template <int TT>
@@ -480,7 +495,7 @@ gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_
     for (int Jt = 0; Jt < ntc; ++Jt) {
       // ---- 1. diagonal tile: unblocked Cholesky in registers
       if (has_tile && I == Jt && J == Jt) {
-#ifdef RVLP_GP_TIMING
+#if defined(RVLP_GP_TIMING) && RVLP_GP_TIMING_SEL < 0
         const long long d0_ = clock64();
 #endif
         double invd[TT];
@@ -522,7 +537,7 @@ gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_
           for (int c = 0; c < TT; ++c) dbuf[r * TT + c] = (c <= r) ? a[r][c] : 0.0;
 #pragma unroll
         for (int c = 0; c < TT; ++c) dbuf[TT * TT + c] = invd[c];
-#ifdef RVLP_GP_TIMING
+#if defined(RVLP_GP_TIMING) && RVLP_GP_TIMING_SEL < 0
         if (blockIdx.x == 0) atomicAdd(&g_gp_timing[9], (unsigned long long)(clock64() - d0_));
 #endif
       }
@@ -530,7 +545,7 @@ gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_
       GPT_LAP(Jt == 0 ? 3 : 4);
       // ---- 2. panel tiles: X L_d^T = A, publish X k-major
       if (has_tile && J == Jt && I > Jt) {
-#ifdef RVLP_GP_TIMING
+#if defined(RVLP_GP_TIMING) && RVLP_GP_TIMING_SEL < 0
         const long long d0_ = clock64();
 #endif
 #pragma unroll
@@ -557,7 +572,7 @@ gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_
         for (int k = 0; k < TT; ++k)
 #pragma unroll
           for (int r = 0; r < TT; ++r) pb[k * TT + r] = a[r][k];
-#ifdef RVLP_GP_TIMING
+#if defined(RVLP_GP_TIMING) && RVLP_GP_TIMING_SEL < 0
         if (blockIdx.x == 0 && I == Jt + 1) atomicAdd(&g_gp_timing[10], (unsigned long long)(clock64() - d0_));
 #endif
       }
@@ -599,14 +614,9 @@ gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_
     }
     __syncthreads();
     GPT_LAP(7);
-#ifdef RVLP_GP_TIMING
-    if (gpt_on) gpt[8] += 1;
-#endif
+    GPT_COUNT();
   }
-#ifdef RVLP_GP_TIMING
-  if (gpt_on)
-    for (int k = 0; k < 16; ++k) atomicAdd(&g_gp_timing[k], gpt[k]);
-#endif
+  GPT_FLUSH();
 }
 
 // ------------------------------------------------------------------ K7: GP conditioning (row f-4)

@@ -1,0 +1,372 @@
+// rvlp_gp_pipe.cuh — K3, software-pipelined register-tile Cholesky (the GP log-posterior of config 5).
+//
+// Same arithmetic per sample as gp_logprob_blocked_kernel (rvlp_gp.cuh: thread (I, J) owns the TT x TT tile of the
+// lower triangle in registers, panel-wise right-looking factorisation, the residual rides along as row N), but the
+// CTA no longer marches through a sample in lock-step.  Phase timing of the lock-step kernel on B200
+// (profiles/r01i_gp_phase_timing.md) showed that per sample ~30 % of the cycles went to work that is NOT part of the
+// factorisation's dependency chain (prior / parameter prologue, the Kepler residual, building the covariance tiles),
+// during which seven of the eight warps were idle or waiting, and that two CTAs per SM overlap almost perfectly
+// (the kernel is latency-bound).  Tiles are handed out column-major, so warp w owns tile columns ~2w .. 2w+2 and has
+// nothing left to do after panel ~2w+1 of 20.  Here a warp RETIRES from a sample after its last panel and starts on
+// the next sample at once:
+//   * the panel barriers are named barriers (bar.sync id, count) whose participant count shrinks as warps retire;
+//     barrier ids alternate with the sample parity, so the early warps of sample s+1 and the late warps of sample s
+//     never meet on the same id;
+//   * warp 0 (retired after panel 1) is the producer of the next sample's record: prior / conversion prologue,
+//     Kepler residual (4 epochs per lane in flight), hyperparameter constants, reject flags; each consumer warp waits
+//     for it on its own two-warp barrier (bar.arrive by the producer, bar.sync by the consumer);
+//   * every warp builds its covariance tiles for sample s+1 as soon as it has retired from s; the per-sample
+//     buffers (record, residual, diagonal tile, partial sums) are double-buffered by sample parity;
+//   * the panel buffer rows are padded to TT*TT + 2 doubles: the 128-bit loads of the trailing update are
+//     bank-conflict free (tools/upd_probe.cu: 1800 -> 1370 cycles per update at two warps per SMSP).
+// Deterministic: fixed tile ownership, fixed summation order inside a tile, the per-panel partial sums
+// (alpha.alpha, pivot mantissa product, pivot exponent sum) are combined by one warp in a fixed butterfly.
+// out[s] depends on (theta[s], epochs) only.
+#pragma once
+#include "rvlp_gp.cuh"
+
+namespace rvlp {
+
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// barrier ids: 0 = __syncthreads (stage_problem only); 1..4 = panel barriers A / B x sample parity;
+// 5 + w = "record of the next sample is ready" for consumer warp w (1 <= w <= 7)
+constexpr int kBarPanel = 1, kBarReady = 5;
+
+// Phase timing (experiments only, -DRVLP_GP_TIMING; tools/gp_pipe_time.py): lane 0 of every warp of CTA 0 adds the
+// cycles since its previous lap to a per-warp shared-memory counter; g_gp_pipe_timing[warp][phase] at kernel end.
+#ifdef RVLP_GP_TIMING
+__device__ unsigned long long g_gp_pipe_timing[64];
+#define PT_DECL unsigned long long* pt_tim = reinterpret_cast<unsigned long long*>(smem + G.off_tim) + warp * 8; \
+  long long pt_t = clock64(); const bool pt_on = blockIdx.x == 0 && lane == 0; if (lane < 8) pt_tim[lane] = 0; __syncwarp();
+#define PT_LAP(k) do { if (pt_on) { const long long n_ = clock64(); pt_tim[k] += (unsigned long long)(n_ - pt_t); pt_t = n_; } } while (0)
+#define PT_FLUSH() do { __syncwarp(); if (blockIdx.x == 0 && lane < 8) atomicAdd(&g_gp_pipe_timing[warp * 8 + lane], pt_tim[lane]); } while (0)
+#else
+#define PT_DECL
+#define PT_LAP(k) do {} while (0)
+#define PT_FLUSH() do {} while (0)
+#endif
+
+struct GpPipeSmem { int off_rec, off_resid, off_ctl, off_d, off_p, off_part, off_tim, pstride, dsize, rsize, total; };
+__host__ __device__ inline GpPipeSmem gp_pipe_smem(const DevProblem& P, const SmemLayout& L, int TT) {
+  GpPipeSmem G;
+  int o = (L.total + 15) & ~15;
+  const int nt = (P.n_epochs + 1 + TT - 1) / TT;
+  const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
+  G.off_rec = o; o += 2 * rec * 8;
+  G.rsize = (P.n_epochs + 2) & ~1;
+  G.off_resid = o; o += 2 * G.rsize * 8;
+  G.off_ctl = o; o += 2 * 8 * 8;                      // per parity: inv_P, inv_le, gamma, A2, flags, pad
+  G.dsize = (TT * TT + TT + 1) & ~1;
+  G.off_d = o; o += 2 * G.dsize * 8;
+  G.pstride = TT * TT + 2;
+  G.off_p = o; o += nt * G.pstride * 8;
+  G.off_part = o; o += 2 * (32 + 192) * 8;            // per parity: alpha.alpha per panel, the pivots (<= 22 * 8)
+  G.off_tim = o; o += 8 * 8 * 8;                      // RVLP_GP_TIMING builds: per-warp phase cycle counters
+  G.total = o;
+  return G;
+}
+
+template <int TT>
+__global__ void __launch_bounds__(kThreads, (TT >= 8 ? 1 : 2))
+gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const SmemLayout L = smem_layout(P);
+  const GpPipeSmem G = gp_pipe_smem(P, L, TT);
+  stage_problem(P, L, smem);                       // the last __syncthreads of the kernel
+  const Tables T = tables_of(P, L, smem);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
+  double* recs = reinterpret_cast<double*>(smem + G.off_rec);
+  double* resids = reinterpret_cast<double*>(smem + G.off_resid);
+  double* ctls = reinterpret_cast<double*>(smem + G.off_ctl);
+  double* dbufs = reinterpret_cast<double*>(smem + G.off_d);
+  double* pbuf = reinterpret_cast<double*>(smem + G.off_p);
+  double* parts = reinterpret_cast<double*>(smem + G.off_part);
+  const int PS = G.pstride;
+  const int N = P.n_epochs;
+  const int nt = (N + 1 + TT - 1) / TT;          // tile rows (incl. the residual row N)
+  const int ntc = (N + TT - 1) / TT;             // panels (columns 0..N-1)
+  const int ntiles = nt * (nt + 1) / 2;
+  const int nwu = (ntiles + 31) >> 5;            // warps that own tiles
+  if (warp >= nwu) return;
+  int J = 0, rem = tid;
+  while (J < nt && rem >= nt - J) { rem -= nt - J; ++J; }
+  const int I = J + rem;
+  const bool has_tile = J < nt;
+  const int r0 = I * TT, c0 = J * TT;
+  const int IN = N / TT, rN = N - IN * TT;       // where the residual row lives
+  // A warp takes part in panel Jt while it owns a tile of column >= Jt, i.e. while its last tile index
+  // (32 warp + 31) is >= the first tile index of column Jt; both the count and my last panel follow from that.
+  int last_panel = -1;
+  for (int Jt = 0; Jt < ntc; ++Jt)
+    if (((Jt * nt - Jt * (Jt - 1) / 2) >> 5) <= warp) last_panel = Jt;
+  const int fin_tile = ((ntc - 1) * nt - (ntc - 1) * (ntc - 2) / 2) + (IN - (ntc - 1));   // tile (IN, ntc-1)
+  const int fin_warp = fin_tile >> 5;
+
+  // ---- producer (warp 0): record, residual, hyperparameter constants and reject flags of sample s2
+  auto produce = [&](int64_t s2, int pb) {
+    double* sr = recs + pb * rec;
+    double* resid = resids + pb * G.rsize;
+    double* ctl = ctls + pb * 8;
+    sample_prologue(P, T, theta, s2, s2 + 1, sr, rec, lane, true, 1);
+    const int flags = __double2loint(sr[1]);
+    int cf = 0;
+    if (flags & (F_JIT | F_HYPER | F_PRIOR)) {               // fit.py:7857-7886: -inf
+      cf = 1;
+    } else {
+      int nonfinite = (flags & F_PLANET) ? 1 : 0;            // fit.py:8022-8024
+      if (!nonfinite) {
+        for (int base = 0; base < N; base += 128) {          // residual v - mean, fit.py:7994-8043, 8059
+          double tt[4], rv[4];
+          int idx[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            idx[j] = base + j * 32 + lane;
+            tt[j] = T.t[idx[j] < N ? idx[j] : N - 1];
+          }
+          model_rv<4>(P, sr, tt, rv, -1, true);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (idx[j] < N) {
+              const double mean = rv[j] + sr[kHdr + T.inst[idx[j]]];
+              if (!(fabs(mean) <= 1.79769313486231570e308)) nonfinite = 1;
+              resid[idx[j]] = T.v[idx[j]] - mean;
+            }
+          }
+        }
+      }
+      if (__any_sync(0xffffffffu, nonfinite)) cf = 2;        // fit.py:8082-8083
+      if (lane == 0) {
+        const double* row = theta + s2 * P.ndim;
+        const GpHyper h = gp_hyper(model_param(T, row, P.n_model + 0), model_param(T, row, P.n_model + 1),
+                                   model_param(T, row, P.n_model + 2), model_param(T, row, P.n_model + 3));
+        ctl[0] = h.inv_P; ctl[1] = h.inv_le; ctl[2] = h.gamma; ctl[3] = h.A2;
+      }
+    }
+    if (lane == 0) ctl[4] = __hiloint2double(0, cf);
+    __threadfence_block();
+    __syncwarp();
+    for (int w = 1; w < nwu; ++w) named_arrive(kBarReady + w, 64);
+  };
+
+  const int64_t stride = gridDim.x;
+  PT_DECL
+  // Trip -1 only produces the first record; trip `it` consumes sample `it` of this CTA and (warp 0) produces the
+  // next one.  One call site: the producer code (priors, conversions, the Kepler solver with its fallbacks) is
+  // 5 000 instructions and must not be duplicated.
+  for (int it = -1;; ++it) {
+    const int64_t s = (int64_t)blockIdx.x + (int64_t)it * stride;
+    const int64_t s_next = s + stride;
+    if (it >= 0) {
+    const int b = it & 1;
+    if (warp != 0) named_sync(kBarReady + warp, 64);
+    PT_LAP(0);
+    const double* sr = recs + b * rec;
+    const double* resid = resids + b * G.rsize;
+    const double* ctl = ctls + b * 8;
+    double* dbuf = dbufs + b * G.dsize;
+    double* part_q = parts + b * (32 + 192), *part_d = part_q + 32;
+    const int barA = kBarPanel + 2 * b, barB = barA + 1;
+    const int cf = __double2loint(ctl[4]);
+    if (cf != 0) {
+      if (tid == 0) {
+        double r = -INFINITY;
+        if (cf == 2) {                                       // non-finite mean model: fit.py:8082-8083
+          r = -INFINITY + sr[0] + sr[4];
+          r += P.jacobian;
+          r += P.renorm;
+        }
+        out[s] = r;
+      }
+      named_sync(barA, nwu * 32);                            // keeps the warps within one sample of each other
+    } else {
+      GpHyper hyp;
+      hyp.inv_P = ctl[0]; hyp.inv_le = ctl[1]; hyp.gamma = ctl[2]; hyp.A2 = ctl[3];
+      double a[TT][TT];                                       // gp.py:145-156, fit.py:8094-8096
+      {
+        // One tile row per trip of a ROLLED loop (TT independent covariance chains in flight), shifted into the
+        // register tile with static indices.  Fully unrolled, the build was 3 000 instructions per thread and -
+        // with the warps of two CTAs in different code regions - instruction-fetch bound (17 k cycles per tile).
+        double tcol[TT];
+#pragma unroll
+        for (int c = 0; c < TT; ++c) tcol[c] = T.t[c0 + c < N ? c0 + c : N - 1];
+#pragma unroll
+        for (int r = 0; r < TT; ++r)
+#pragma unroll
+          for (int c = 0; c < TT; ++c) a[r][c] = 0.0;
+#pragma unroll 1
+        for (int r = 0; r < TT; ++r) {
+          const int i = r0 + r;
+          const int ic = i < N ? i : N - 1;
+          const double ti = T.t[ic];
+          const bool cov_row = has_tile && i < N;
+          const bool res_row = has_tile && i == N;
+          const double dterm = T.e2[ic] + sr[kHdr + P.n_inst + T.inst[ic]];   // fit.py:8094-8096
+          double row[TT];
+#pragma unroll
+          for (int c = 0; c < TT; ++c) row[c] = gp_cov(ti - tcol[c], hyp);     // branch-free (rvlp_gpcov.cuh)
+#pragma unroll
+          for (int c = 0; c < TT; ++c) {
+            const int k = c0 + c;
+            double v = (cov_row && k <= i) ? row[c] : 0.0;
+            if (cov_row && k == i) v += dterm;
+            if (res_row && k < N) v = resid[k];
+            if (has_tile && i >= N && k == i) v = 1.0;         // identity padding: the diagonal-tile code needs no masks
+            row[c] = v;
+          }
+#pragma unroll
+          for (int q = 0; q + 1 < TT; ++q)
+#pragma unroll
+            for (int c = 0; c < TT; ++c) a[q][c] = a[q + 1][c];
+#pragma unroll
+          for (int c = 0; c < TT; ++c) a[TT - 1][c] = row[c];
+        }
+      }
+      PT_LAP(1);
+      for (int Jt = 0; Jt <= last_panel; ++Jt) {
+        const int nsync = (nwu - ((Jt * nt - Jt * (Jt - 1) / 2) >> 5)) * 32;
+        // ---- 1. diagonal tile: unblocked Cholesky in registers.  One thread works and the panel waits, so this
+        //         is the shortest instruction sequence that does it: the pivots go to shared memory as they are (the
+        //         log-determinant is formed once per sample by the finishing warp), padding rows / columns are an
+        //         identity block by construction, only the lower triangle is published.
+        if (has_tile && I == Jt && J == Jt) {
+          double invd[TT];
+#pragma unroll
+          for (int c = 0; c < TT; ++c) {
+            // columns >= N (last panel when TT does not divide N) are an identity block: zero below the diagonal by
+            // construction; only the pivot is masked, because the residual row has updated "its" diagonal element
+            const double d = c0 + c < N ? a[c][c] : 1.0;
+            part_d[Jt * TT + c] = d;
+            const double inv = pivot_rsqrt(d);                   // NaN when not positive definite (as jax)
+            invd[c] = inv;
+            a[c][c] = d * inv;
+#pragma unroll
+            for (int r = c + 1; r < TT; ++r) a[r][c] *= inv;
+#pragma unroll
+            for (int r = c + 1; r < TT; ++r)
+#pragma unroll
+              for (int k = c + 1; k <= r; ++k) a[r][k] = fma(-a[r][c], a[k][c], a[r][k]);
+          }
+          if (IN == Jt) {                                        // the residual row sits in this tile
+            double quad = 0.0;
+#pragma unroll
+            for (int r = 0; r < TT; ++r)
+              if (r == rN) {
+#pragma unroll
+                for (int c = 0; c < TT; ++c)
+                  if (c < r) quad = fma(a[r][c], a[r][c], quad);
+              }
+            part_q[Jt] = quad;
+          }
+#pragma unroll
+          for (int r = 0; r < TT; ++r)
+#pragma unroll
+            for (int c = 0; c < TT; ++c)
+              if (c < r) dbuf[r * TT + c] = a[r][c];
+#pragma unroll
+          for (int c = 0; c < TT; ++c) dbuf[TT * TT + c] = invd[c];
+        }
+        PT_LAP(2);
+        named_sync(barA, nsync);
+        PT_LAP(3);
+        // ---- 2. panel tiles: X L_d^T = A, publish X k-major
+        if (has_tile && J == Jt && I > Jt) {
+#pragma unroll
+          for (int c = 0; c < TT; ++c) {
+            const double inv = dbuf[TT * TT + c];
+#pragma unroll
+            for (int r = 0; r < TT; ++r) {
+              double x = a[r][c];
+#pragma unroll
+              for (int k = 0; k < c; ++k) x = fma(-a[r][k], dbuf[c * TT + k], x);
+              a[r][c] = x * inv;
+            }
+          }
+          if (I == IN) {                                         // alpha_j for this panel's columns
+            double quad = 0.0;
+#pragma unroll
+            for (int r = 0; r < TT; ++r)
+              if (r == rN) {
+#pragma unroll
+                for (int c = 0; c < TT; ++c) quad = fma(a[r][c], a[r][c], quad);
+              }
+            part_q[Jt] = quad;
+          }
+          double2* pb = reinterpret_cast<double2*>(pbuf + I * PS);
+#pragma unroll
+          for (int k = 0; k < TT; ++k)
+#pragma unroll
+            for (int r = 0; r < TT; r += 2) pb[(k * TT + r) / 2] = make_double2(a[r][k], a[r + 1][k]);
+        }
+        named_sync(barB, nsync);
+        PT_LAP(4);
+        // ---- 3. trailing tiles: a -= P_I P_J^T
+        if (has_tile && J > Jt) {
+          const double2* pi = reinterpret_cast<const double2*>(pbuf + I * PS);
+          const double2* pj = reinterpret_cast<const double2*>(pbuf + J * PS);
+#pragma unroll
+          for (int k = 0; k < TT; ++k) {
+            double Li[TT], Lk[TT];
+#pragma unroll
+            for (int r = 0; r < TT; r += 2) {
+              const double2 u = pi[(k * TT + r) / 2], w = pj[(k * TT + r) / 2];
+              Li[r] = u.x; Li[r + 1] = u.y;
+              Lk[r] = w.x; Lk[r + 1] = w.y;
+            }
+#pragma unroll
+            for (int r = 0; r < TT; ++r)
+#pragma unroll
+              for (int c = 0; c < TT; ++c) a[r][c] = fma(-Li[r], Lk[c], a[r][c]);
+          }
+        }
+        PT_LAP(5);
+      }
+      // ---- the warp that saw the last panel combines the per-panel partial sums (fixed butterfly)
+      if (warp == fin_warp) {
+        double q = lane < ntc ? part_q[lane] : 0.0;
+        // sum_j ln L_jj = 1/2 ln prod_j piv_j: running product of the pivots' mantissas + integer exponent sum,
+        // one log per sample; a zero / negative / NaN pivot goes into the product as it is (log says so)
+        double m = 1.0;
+        int ex = 0;
+        for (int j = lane; j < ntc * TT; j += 32) {
+          const double d = part_d[j];
+          const int h = __double2hiint(d);
+          if ((unsigned)(h - 0x00100000) < 0x7fe00000u) {
+            m *= __hiloint2double((h & 0x000fffff) | 0x3ff00000, __double2loint(d));
+            ex += (h >> 20) - 1023;
+          } else {
+            m *= d;
+          }
+        }
+        double e = (double)ex;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          q += __shfl_xor_sync(0xffffffffu, q, o);
+          m *= __shfl_xor_sync(0xffffffffu, m, o);
+          e += __shfl_xor_sync(0xffffffffu, e, o);
+        }
+        if (lane == 0) {
+          const double logdet = 0.5 * fma(e, 0.6931471805599453, log(m));   // sum_j ln L_jj = 1/2 ln prod piv_j
+          const double ll = -0.5 * q - logdet - 0.5 * (double)N * kLog2Pi;
+          double r = ll + sr[0] + sr[4];                                    // fit.py:7898-7900
+          r += P.jacobian;
+          r += P.renorm;
+          out[s] = r;
+        }
+      }
+    }
+    PT_LAP(7);
+    }
+    if (s_next >= S) break;
+    if (warp == 0) produce(s_next, (it + 1) & 1);
+    PT_LAP(6);
+  }
+  PT_FLUSH();
+}
+
+}  // namespace rvlp
