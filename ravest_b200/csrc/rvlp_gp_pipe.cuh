@@ -30,12 +30,18 @@ namespace rvlp {
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// keeps a loop-invariant integer in a register: without it the compiler rematerialises shared-memory offsets from
+// the kernel parameters after every barrier (a 30-instruction dependent chain per panel)
+__device__ __forceinline__ void opaque_i32(const int& v) { asm volatile("" : "+r"(const_cast<int&>(v))); }
 __device__ __forceinline__ void named_arrive(int id, int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 // barrier ids: 0 = __syncthreads (stage_problem only); 1..4 = panel barriers A / B x sample parity;
-// 5 + w = "record of the next sample is ready" for consumer warp w (1 <= w <= 7)
+// 5 + r = "record of the next sample is ready" for the consumer warp of role r (1 <= r <= 7)
 constexpr int kBarPanel = 1, kBarReady = 5;
+#ifndef RVLP_GP_ABLATE
+#define RVLP_GP_ABLATE 0   /* experiments: 1 no diag arithmetic, 2 no TRSM arithmetic, 3 no update, 4 no covariance build */
+#endif
 
 // Phase timing (experiments only, -DRVLP_GP_TIMING; tools/gp_pipe_time.py): lane 0 of every warp of CTA 0 adds the
 // cycles since its previous lap to a per-warp shared-memory counter; g_gp_pipe_timing[warp][phase] at kernel end.
@@ -64,7 +70,7 @@ __host__ __device__ inline GpPipeSmem gp_pipe_smem(const DevProblem& P, const Sm
   G.dsize = (TT * TT + TT + 1) & ~1;
   G.off_d = o; o += 2 * G.dsize * 8;
   G.pstride = TT * TT + 2;
-  G.off_p = o; o += nt * G.pstride * 8;
+  G.off_p = o; o += 4 * nt * G.pstride * 8;            // (sample parity, panel parity) x tile rows
   G.off_part = o; o += 2 * (32 + 192) * 8;            // per parity: alpha.alpha per panel, the pivots (<= 22 * 8)
   G.off_tim = o; o += 8 * 8 * 8;                      // RVLP_GP_TIMING builds: per-warp phase cycle counters
   G.total = o;
@@ -85,7 +91,6 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
   double* resids = reinterpret_cast<double*>(smem + G.off_resid);
   double* ctls = reinterpret_cast<double*>(smem + G.off_ctl);
   double* dbufs = reinterpret_cast<double*>(smem + G.off_d);
-  double* pbuf = reinterpret_cast<double*>(smem + G.off_p);
   double* parts = reinterpret_cast<double*>(smem + G.off_part);
   const int PS = G.pstride;
   const int N = P.n_epochs;
@@ -94,19 +99,31 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
   const int ntiles = nt * (nt + 1) / 2;
   const int nwu = (ntiles + 31) >> 5;            // warps that own tiles
   if (warp >= nwu) return;
-  int J = 0, rem = tid;
+  // role r = the r-th warp-sized slice of the column-major tile list (role 0 retires first, role nwu-1 last).
+  // Warp w sits on SM sub-partition w % 4: pair the latest roles with the earliest ones on each sub-partition
+  // (trailing-update work per role ~ 2, 4, 6, 8, 10, 13, 18, 20 panels at N = 120: 28 on the busiest
+  // sub-partition with role = warp, 22 with this pairing).
+  const int role = warp < (nwu < 4 ? nwu : 4) ? nwu - 1 - warp : warp - 4;
+  opaque_i32(role);
+  const int rid = role * 32 + lane;
+  int J = 0, rem = rid;
   while (J < nt && rem >= nt - J) { rem -= nt - J; ++J; }
   const int I = J + rem;
   const bool has_tile = J < nt;
   const int r0 = I * TT, c0 = J * TT;
   const int IN = N / TT, rN = N - IN * TT;       // where the residual row lives
+  const int pbytes = nt * PS * 8;                // one panel buffer
+  const int pi_off = G.off_p + I * PS * 8, pj_off = G.off_p + (J < nt ? J : 0) * PS * 8;
+  opaque_i32(pi_off);
+  opaque_i32(pj_off);
+  opaque_i32(pbytes);
   // A warp takes part in panel Jt while it owns a tile of column >= Jt, i.e. while its last tile index
   // (32 warp + 31) is >= the first tile index of column Jt; both the count and my last panel follow from that.
   int last_panel = -1;
   for (int Jt = 0; Jt < ntc; ++Jt)
-    if (((Jt * nt - Jt * (Jt - 1) / 2) >> 5) <= warp) last_panel = Jt;
+    if (((Jt * nt - Jt * (Jt - 1) / 2) >> 5) <= role) last_panel = Jt;
   const int fin_tile = ((ntc - 1) * nt - (ntc - 1) * (ntc - 2) / 2) + (IN - (ntc - 1));   // tile (IN, ntc-1)
-  const int fin_warp = fin_tile >> 5;
+  const int fin_role = fin_tile >> 5;
 
   // ---- producer (warp 0): record, residual, hyperparameter constants and reject flags of sample s2
   auto produce = [&](int64_t s2, int pb) {
@@ -164,7 +181,7 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
     const int64_t s_next = s + stride;
     if (it >= 0) {
     const int b = it & 1;
-    if (warp != 0) named_sync(kBarReady + warp, 64);
+    if (role != 0) named_sync(kBarReady + role, 64);
     PT_LAP(0);
     const double* sr = recs + b * rec;
     const double* resid = resids + b * G.rsize;
@@ -174,7 +191,7 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
     const int barA = kBarPanel + 2 * b, barB = barA + 1;
     const int cf = __double2loint(ctl[4]);
     if (cf != 0) {
-      if (tid == 0) {
+      if (rid == 0) {
         double r = -INFINITY;
         if (cf == 2) {                                       // non-finite mean model: fit.py:8082-8083
           r = -INFINITY + sr[0] + sr[4];
@@ -209,7 +226,8 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
           const double dterm = T.e2[ic] + sr[kHdr + P.n_inst + T.inst[ic]];   // fit.py:8094-8096
           double row[TT];
 #pragma unroll
-          for (int c = 0; c < TT; ++c) row[c] = gp_cov(ti - tcol[c], hyp);     // branch-free (rvlp_gpcov.cuh)
+          for (int c = 0; c < TT; ++c)
+            row[c] = RVLP_GP_ABLATE == 4 ? ti - tcol[c] : gp_cov(ti - tcol[c], hyp);     // branch-free (rvlp_gpcov.cuh)
 #pragma unroll
           for (int c = 0; c < TT; ++c) {
             const int k = c0 + c;
@@ -242,6 +260,10 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
             // construction; only the pivot is masked, because the residual row has updated "its" diagonal element
             const double d = c0 + c < N ? a[c][c] : 1.0;
             part_d[Jt * TT + c] = d;
+#if RVLP_GP_ABLATE == 1
+            const double inv = 1.0;
+            invd[c] = inv;
+#else
             const double inv = pivot_rsqrt(d);                   // NaN when not positive definite (as jax)
             invd[c] = inv;
             a[c][c] = d * inv;
@@ -251,6 +273,7 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
             for (int r = c + 1; r < TT; ++r)
 #pragma unroll
               for (int k = c + 1; k <= r; ++k) a[r][k] = fma(-a[r][c], a[k][c], a[r][k]);
+#endif
           }
           if (IN == Jt) {                                        // the residual row sits in this tile
             double quad = 0.0;
@@ -272,7 +295,17 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
           for (int c = 0; c < TT; ++c) dbuf[TT * TT + c] = invd[c];
         }
         PT_LAP(2);
-        named_sync(barA, nsync);
+        {
+          // only the roles that own tiles of column Jt wait for the diagonal tile; everybody else goes straight to
+          // barrier B.  (The panel buffers alternate with the panel parity, so a panel is never overwritten while a
+          // slower warp still reads the previous one.)
+          const int t0 = Jt * nt - Jt * (Jt - 1) / 2;
+          const int wa = t0 >> 5, wb = (t0 + nt - Jt - 1) >> 5;
+          if (role >= wa && role <= wb) {
+            if (wa == wb) __syncwarp();
+            else named_sync(barA, (wb - wa + 1) * 32);
+          }
+        }
         PT_LAP(3);
         // ---- 2. panel tiles: X L_d^T = A, publish X k-major
         if (has_tile && J == Jt && I > Jt) {
@@ -281,10 +314,14 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
             const double inv = dbuf[TT * TT + c];
 #pragma unroll
             for (int r = 0; r < TT; ++r) {
+#if RVLP_GP_ABLATE == 2
+              a[r][c] += inv;
+#else
               double x = a[r][c];
 #pragma unroll
               for (int k = 0; k < c; ++k) x = fma(-a[r][k], dbuf[c * TT + k], x);
               a[r][c] = x * inv;
+#endif
             }
           }
           if (I == IN) {                                         // alpha_j for this panel's columns
@@ -297,7 +334,7 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
               }
             part_q[Jt] = quad;
           }
-          double2* pb = reinterpret_cast<double2*>(pbuf + I * PS);
+          double2* pb = reinterpret_cast<double2*>(smem + pi_off + (2 * b + (Jt & 1)) * pbytes);
 #pragma unroll
           for (int k = 0; k < TT; ++k)
 #pragma unroll
@@ -306,9 +343,9 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
         named_sync(barB, nsync);
         PT_LAP(4);
         // ---- 3. trailing tiles: a -= P_I P_J^T
-        if (has_tile && J > Jt) {
-          const double2* pi = reinterpret_cast<const double2*>(pbuf + I * PS);
-          const double2* pj = reinterpret_cast<const double2*>(pbuf + J * PS);
+        if (has_tile && J > Jt && RVLP_GP_ABLATE != 3) {
+          const double2* pi = reinterpret_cast<const double2*>(smem + pi_off + (2 * b + (Jt & 1)) * pbytes);
+          const double2* pj = reinterpret_cast<const double2*>(smem + pj_off + (2 * b + (Jt & 1)) * pbytes);
 #pragma unroll
           for (int k = 0; k < TT; ++k) {
             double Li[TT], Lk[TT];
@@ -327,7 +364,7 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
         PT_LAP(5);
       }
       // ---- the warp that saw the last panel combines the per-panel partial sums (fixed butterfly)
-      if (warp == fin_warp) {
+      if (role == fin_role) {
         double q = lane < ntc ? part_q[lane] : 0.0;
         // sum_j ln L_jj = 1/2 ln prod_j piv_j: running product of the pivots' mantissas + integer exponent sum,
         // one log per sample; a zero / negative / NaN pivot goes into the product as it is (log says so)
@@ -363,7 +400,7 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
     PT_LAP(7);
     }
     if (s_next >= S) break;
-    if (warp == 0) produce(s_next, (it + 1) & 1);
+    if (role == 0) produce(s_next, (it + 1) & 1);
     PT_LAP(6);
   }
   PT_FLUSH();
