@@ -121,7 +121,9 @@ struct rvlp_ctx {
   void* d_src_const = nullptr;
   void* d_priors = nullptr;
   void* d_epochs = nullptr;
-  int smem_main = 0, smem_gp = 0, smem_gp_tiled = 0, smem_gp_blocked = 0, smem_gp_pipe = 0, gp_tile = 0, smem_gp_predict = 0;
+  int smem_main = 0, smem_gp = 0, smem_gp_tiled = 0, smem_gp_blocked = 0, smem_gp_pipe = 0, smem_gp_pipe_pred = 0, gp_tile = 0, smem_gp_predict = 0;
+  double* d_beta = nullptr;      // K7 scratch: beta = C^-1 r per sample, [beta_rows, n_epochs]
+  int64_t beta_rows = 0;
   int max_smem = 0;
   int k1 = 0;          // K1 variant in use
   int k1_tuned = 0;    // rvlp_ctx_autotune has run
@@ -250,10 +252,12 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
     c->smem_gp_tiled = gp_tiled_smem(P, L).total;
     c->smem_gp_blocked = c->gp_tile ? gp_blocked_smem(P, L, c->gp_tile).total : 0;
     c->smem_gp_pipe = c->gp_tile ? gp_pipe_smem(P, L, c->gp_tile).total : 0;
-    CTX_TRY(cudaFuncSetAttribute(gp_logprob_pipe_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-    CTX_TRY(cudaFuncSetAttribute(gp_logprob_pipe_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-    CTX_TRY(cudaFuncSetAttribute(gp_logprob_pipe_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-    CTX_TRY(cudaFuncSetAttribute(gp_logprob_pipe_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    c->smem_gp_pipe_pred = c->gp_tile ? gp_pipe_smem(P, L, c->gp_tile, true).total : 0;
+#define RVLP_GP_ATTR(TT)                                                                                                 \
+    CTX_TRY(cudaFuncSetAttribute(gp_logprob_pipe_kernel<TT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem)); \
+    CTX_TRY(cudaFuncSetAttribute(gp_logprob_pipe_kernel<TT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    RVLP_GP_ATTR(2) RVLP_GP_ATTR(4) RVLP_GP_ATTR(6) RVLP_GP_ATTR(8)
+#undef RVLP_GP_ATTR
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_blocked_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
@@ -281,6 +285,7 @@ void rvlp_ctx_destroy(rvlp_ctx* c) {
   cudaFree(c->d_theta);
   cudaFree(c->d_out);
   cudaFree(c->d_tickets);
+  cudaFree(c->d_beta);
   if (c->h_theta) cudaFreeHost(c->h_theta);
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -512,10 +517,10 @@ int rvlp_gp_logprob_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
 #define RVLP_GP_TILED(TT)                                                                                   \
   case TT:                                                                                                  \
     if (use_pipe) {                                                                                         \
-      rc = grid_for(c->device, (const void*)gp_logprob_pipe_kernel<TT>, c->smem_gp_pipe, S, &grid);         \
+      rc = grid_for(c->device, (const void*)gp_logprob_pipe_kernel<TT, false>, c->smem_gp_pipe, S, &grid);  \
       if (rc) return rc;                                                                                    \
       if (grid_cap && atoi(grid_cap) > 0 && atoi(grid_cap) < grid) grid = atoi(grid_cap);                   \
-      gp_logprob_pipe_kernel<TT><<<grid, kThreads, c->smem_gp_pipe, st>>>(c->P, theta_dev, S, out_dev);     \
+      gp_logprob_pipe_kernel<TT, false><<<grid, kThreads, c->smem_gp_pipe, st>>>(c->P, theta_dev, S, out_dev, nullptr); \
     } else if (use_column) {                                                                                \
       rc = grid_for(c->device, (const void*)gp_logprob_tiled_kernel<TT>, c->smem_gp_tiled, S, &grid);       \
       if (rc) return rc;                                                                                    \
@@ -567,6 +572,45 @@ int rvlp_gp_predict_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const
   if (c->P.n_hyper != 4) return fail(RVLP_EINVAL, "context was not created with GP hyperparameters");
   if (T > 0 && (!times_dev || !mean_dev)) return fail(RVLP_EINVAL, "null times / mean pointer");
   if (S == 0 || (T == 0 && !chi2_dev)) return RVLP_OK;
+  // Product path for N <= 175 epochs: the pipelined register-tile factorisation with the factor kept in shared memory
+  // and a blocked back substitution (beta = C^-1 r into a context-owned scratch), then the conditional-mean kernel.
+  // RVLP_GP_KERNEL=smem selects the older single kernel (cross-checks).
+  const char* which = getenv("RVLP_GP_KERNEL");
+  if (c->gp_tile && c->smem_gp_pipe_pred <= c->max_smem && !(which && !strcmp(which, "smem"))) {
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = c->P.n_epochs;
+    if (c->beta_rows < S) {                       // grow-only scratch; reallocation synchronises, steady state does not
+      CUDA_TRY(cudaStreamSynchronize(st));
+      cudaFree(c->d_beta);
+      c->d_beta = nullptr; c->beta_rows = 0;
+      CUDA_TRY(cudaMalloc((void**)&c->d_beta, sizeof(double) * (size_t)S * N));
+      c->beta_rows = S;
+    }
+    int grid = 0, rc = RVLP_OK;
+#define RVLP_GP_PRED(TT)                                                                                          \
+  case TT:                                                                                                        \
+    rc = grid_for(c->device, (const void*)gp_logprob_pipe_kernel<TT, true>, c->smem_gp_pipe_pred, S, &grid);      \
+    if (rc) return rc;                                                                                            \
+    gp_logprob_pipe_kernel<TT, true><<<grid, kThreads, c->smem_gp_pipe_pred, st>>>(c->P, theta_dev, S, chi2_dev, c->d_beta); \
+    break;
+    switch (c->gp_tile) {
+      RVLP_GP_PRED(2) RVLP_GP_PRED(4) RVLP_GP_PRED(6) RVLP_GP_PRED(8)
+      default: return fail(RVLP_EUNSUPPORTED, "no GP tile size for %d epochs", N);
+    }
+#undef RVLP_GP_PRED
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    if (T > 0) {
+      const int smem_mean = 2 * ((N + 1) & ~1) * 8;
+      rc = grid_for(c->device, (const void*)gp_mean_kernel, smem_mean, S, &grid);
+      if (rc) return rc;
+      gp_mean_kernel<<<grid, kThreads, smem_mean, st>>>(c->P, theta_dev, S, c->d_beta, times_dev, T, mean_dev);
+      ++g_launches;
+      CUDA_TRY(cudaGetLastError());
+    }
+    return RVLP_OK;
+  }
   if (c->smem_gp_predict > c->max_smem)
     return fail(RVLP_EUNSUPPORTED, "GP conditioning needs %d B of shared memory per CTA (> %d): too many epochs",
                 c->smem_gp_predict, c->max_smem);

@@ -57,32 +57,41 @@ __device__ unsigned long long g_gp_pipe_timing[64];
 #define PT_FLUSH() do {} while (0)
 #endif
 
-struct GpPipeSmem { int off_rec, off_resid, off_ctl, off_d, off_p, off_part, off_tim, pstride, dsize, rsize, total; };
-__host__ __device__ inline GpPipeSmem gp_pipe_smem(const DevProblem& P, const SmemLayout& L, int TT) {
+struct GpPipeSmem { int off_rec, off_resid, off_ctl, off_d, off_p, off_part, off_beta, off_tim, pstride, dsize, rsize, total; };
+// pred: the conditioning variant keeps EVERY panel (the whole factor L, tile-packed: panel p holds tile rows p+1 .. nt-1)
+// and every diagonal tile until the sample's back substitution is done, instead of two alternating panel buffers.
+__host__ __device__ inline GpPipeSmem gp_pipe_smem(const DevProblem& P, const SmemLayout& L, int TT, bool pred = false) {
   GpPipeSmem G;
   int o = (L.total + 15) & ~15;
   const int nt = (P.n_epochs + 1 + TT - 1) / TT;
+  const int ntc = (P.n_epochs + TT - 1) / TT;
   const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
   G.off_rec = o; o += 2 * rec * 8;
   G.rsize = (P.n_epochs + 2) & ~1;
   G.off_resid = o; o += 2 * G.rsize * 8;
   G.off_ctl = o; o += 2 * 8 * 8;                      // per parity: inv_P, inv_le, gamma, A2, flags, pad
   G.dsize = (TT * TT + TT + 1) & ~1;
-  G.off_d = o; o += 2 * G.dsize * 8;
+  G.off_d = o; o += (pred ? ntc : 2) * G.dsize * 8;
   G.pstride = TT * TT + 2;
-  G.off_p = o; o += 4 * nt * G.pstride * 8;            // (sample parity, panel parity) x tile rows
+  G.off_p = o; o += (pred ? nt * (nt - 1) / 2 : 4 * nt) * G.pstride * 8;   // else (sample parity, panel parity) x tile rows
   G.off_part = o; o += 2 * (32 + 192) * 8;            // per parity: alpha.alpha per panel, the pivots (<= 22 * 8)
+  G.off_beta = o; o += (pred ? ntc * TT : 0) * 8;
   G.off_tim = o; o += 8 * 8 * 8;                      // RVLP_GP_TIMING builds: per-warp phase cycle counters
   G.total = o;
   return G;
 }
 
-template <int TT>
+// PRED = false: K3, out[s] = GP log-posterior.  PRED = true: the solve half of K7 (row f-4): no priors, the residual of
+// GPFitter's predictions ((v - gamma) - planets - trend, fit.py:6375-6380, 7536-7550), out[s] = chi^2 = alpha.alpha
+// (fit.py:5428-5429, may be null) and beta_out[s, :] = C^-1 r = L^-T alpha for gp_mean_kernel; a sample the reference
+// raises for (invalid planet / hyperparameters) gives NaN rows.
+template <int TT, bool PRED>
 __global__ void __launch_bounds__(kThreads, (TT >= 8 ? 1 : 2))
-gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double* __restrict__ out) {
+gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double* __restrict__ out,
+                       double* __restrict__ beta_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = smem_layout(P);
-  const GpPipeSmem G = gp_pipe_smem(P, L, TT);
+  const GpPipeSmem G = gp_pipe_smem(P, L, TT, PRED);
   stage_problem(P, L, smem);                       // the last __syncthreads of the kernel
   const Tables T = tables_of(P, L, smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -130,13 +139,13 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
     double* sr = recs + pb * rec;
     double* resid = resids + pb * G.rsize;
     double* ctl = ctls + pb * 8;
-    sample_prologue(P, T, theta, s2, s2 + 1, sr, rec, lane, true, 1);
+    sample_prologue(P, T, theta, s2, s2 + 1, sr, rec, lane, !PRED, 1);
     const int flags = __double2loint(sr[1]);
     int cf = 0;
-    if (flags & (F_JIT | F_HYPER | F_PRIOR)) {               // fit.py:7857-7886: -inf
-      cf = 1;
+    if (PRED ? (flags & (F_PLANET | F_HYPER)) : (flags & (F_JIT | F_HYPER | F_PRIOR))) {
+      cf = 1;                                                // fit.py:7857-7886: -inf (PRED: the reference raises -> NaN)
     } else {
-      int nonfinite = (flags & F_PLANET) ? 1 : 0;            // fit.py:8022-8024
+      int nonfinite = (!PRED && (flags & F_PLANET)) ? 1 : 0; // fit.py:8022-8024
       if (!nonfinite) {
         for (int base = 0; base < N; base += 128) {          // residual v - mean, fit.py:7994-8043, 8059
           double tt[4], rv[4];
@@ -150,9 +159,13 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if (idx[j] < N) {
-              const double mean = rv[j] + sr[kHdr + T.inst[idx[j]]];
-              if (!(fabs(mean) <= 1.79769313486231570e308)) nonfinite = 1;
-              resid[idx[j]] = T.v[idx[j]] - mean;
+              if (PRED) {
+                resid[idx[j]] = (T.v[idx[j]] - sr[kHdr + T.inst[idx[j]]]) - rv[j];
+              } else {
+                const double mean = rv[j] + sr[kHdr + T.inst[idx[j]]];
+                if (!(fabs(mean) <= 1.79769313486231570e308)) nonfinite = 1;
+                resid[idx[j]] = T.v[idx[j]] - mean;
+              }
             }
           }
         }
@@ -186,12 +199,18 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
     const double* sr = recs + b * rec;
     const double* resid = resids + b * G.rsize;
     const double* ctl = ctls + b * 8;
-    double* dbuf = dbufs + b * G.dsize;
+    double* dbuf = dbufs + (PRED ? 0 : b * G.dsize);         // PRED: + Jt * dsize inside the panel loop
     double* part_q = parts + b * (32 + 192), *part_d = part_q + 32;
     const int barA = kBarPanel + 2 * b, barB = barA + 1;
     const int cf = __double2loint(ctl[4]);
     if (cf != 0) {
-      if (rid == 0) {
+      if (PRED) {
+        if (role == 0) {
+          const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+          for (int j = lane; j < N; j += 32) beta_out[s * N + j] = qnan;
+          if (lane == 0 && out) out[s] = qnan;
+        }
+      } else if (rid == 0) {
         double r = -INFINITY;
         if (cf == 2) {                                       // non-finite mean model: fit.py:8082-8083
           r = -INFINITY + sr[0] + sr[4];
@@ -246,8 +265,14 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
         }
       }
       PT_LAP(1);
+      // PRED: the factor of the previous sample stays in shared memory until its back substitution is done
+      if (PRED) named_sync(barB, nwu * 32);
       for (int Jt = 0; Jt <= last_panel; ++Jt) {
         const int nsync = (nwu - ((Jt * nt - Jt * (Jt - 1) / 2) >> 5)) * 32;
+        if (PRED) dbuf = dbufs + Jt * G.dsize;
+        // byte offset of this panel's buffer relative to row 0 of buffer 0 (pi_off / pj_off address row I / J there).
+        // PRED: panel Jt holds tile rows Jt+1 .. nt-1 packed behind the earlier panels.
+        const int pshift = PRED ? (Jt * (nt - 1) - Jt * (Jt - 1) / 2 - Jt - 1) * PS * 8 : (2 * b + (Jt & 1)) * pbytes;
         // ---- 1. diagonal tile: unblocked Cholesky in registers.  One thread works and the panel waits, so this
         //         is the shortest instruction sequence that does it: the pivots go to shared memory as they are (the
         //         log-determinant is formed once per sample by the finishing warp), padding rows / columns are an
@@ -334,7 +359,7 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
               }
             part_q[Jt] = quad;
           }
-          double2* pb = reinterpret_cast<double2*>(smem + pi_off + (2 * b + (Jt & 1)) * pbytes);
+          double2* pb = reinterpret_cast<double2*>(smem + pi_off + pshift);
 #pragma unroll
           for (int k = 0; k < TT; ++k)
 #pragma unroll
@@ -344,8 +369,8 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
         PT_LAP(4);
         // ---- 3. trailing tiles: a -= P_I P_J^T
         if (has_tile && J > Jt && RVLP_GP_ABLATE != 3) {
-          const double2* pi = reinterpret_cast<const double2*>(smem + pi_off + (2 * b + (Jt & 1)) * pbytes);
-          const double2* pj = reinterpret_cast<const double2*>(smem + pj_off + (2 * b + (Jt & 1)) * pbytes);
+          const double2* pi = reinterpret_cast<const double2*>(smem + pi_off + pshift);
+          const double2* pj = reinterpret_cast<const double2*>(smem + pj_off + pshift);
 #pragma unroll
           for (int k = 0; k < TT; ++k) {
             double Li[TT], Lk[TT];
@@ -387,7 +412,51 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
           m *= __shfl_xor_sync(0xffffffffu, m, o);
           e += __shfl_xor_sync(0xffffffffu, e, o);
         }
-        if (lane == 0) {
+        if (PRED) {
+          // ---- beta = L^-T alpha, one warp, tile column by tile column from the last one (fit.py:6407-6414, 7536-7554:
+          //      gp.condition(...).gp.mean = K(t*, t) C^-1 r).  z starts as alpha (the residual row of every panel), the
+          //      TT x TT triangular solve is done redundantly by every lane (operands are shared-memory broadcasts),
+          //      then the lanes share the update z_J' -= L_{J,J'}^T beta_J of the earlier columns.
+          double* bvec = reinterpret_cast<double*>(smem + G.off_beta);
+          const double* Lp = reinterpret_cast<const double*>(smem + G.off_p);
+          for (int j = lane; j < ntc * TT; j += 32) {
+            const int pp = j / TT, k = j - pp * TT;
+            double z = 0.0;
+            if (j < N)
+              z = IN == pp ? dbufs[pp * G.dsize + rN * TT + k]
+                           : Lp[(pp * (nt - 1) - pp * (pp - 1) / 2 + IN - pp - 1) * PS + k * TT + rN];
+            bvec[j] = z;
+          }
+          __syncwarp();
+          for (int Jb = ntc - 1; Jb >= 0; --Jb) {
+            const double* Ld = dbufs + Jb * G.dsize;
+            const int nreal = N - Jb * TT < TT ? N - Jb * TT : TT;
+            double bj[TT];
+#pragma unroll
+            for (int c = TT - 1; c >= 0; --c) {
+              double x = bvec[Jb * TT + c];
+#pragma unroll
+              for (int r = c + 1; r < TT; ++r) x = fma(-Ld[r * TT + c], bj[r], x);
+              bj[c] = c < nreal ? x * Ld[TT * TT + c] : 0.0;
+            }
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+              for (int c = 0; c < TT; ++c) bvec[Jb * TT + c] = bj[c];
+            }
+            for (int e = lane; e < Jb * TT; e += 32) {
+              const int pp = e / TT, k = e - pp * TT;
+              const double* Lt = Lp + (pp * (nt - 1) - pp * (pp - 1) / 2 + Jb - pp - 1) * PS + k * TT;   // L[Jb*TT + r][pp*TT + k]
+              double z = bvec[e];
+#pragma unroll
+              for (int r = 0; r < TT; ++r) z = fma(-Lt[r], bj[r], z);
+              bvec[e] = z;
+            }
+            __syncwarp();
+          }
+          for (int j = lane; j < N; j += 32) beta_out[s * N + j] = bvec[j];
+          if (lane == 0 && out) out[s] = q;                                   // chi^2 = alpha.alpha
+        } else if (lane == 0) {
           const double logdet = 0.5 * fma(e, 0.6931471805599453, log(m));   // sum_j ln L_jj = 1/2 ln prod piv_j
           const double ll = -0.5 * q - logdet - 0.5 * (double)N * kLog2Pi;
           double r = ll + sr[0] + sr[4];                                    // fit.py:7898-7900
@@ -404,6 +473,41 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
     PT_LAP(6);
   }
   PT_FLUSH();
+}
+
+// ------------------------------------------------------------------ K7b: conditional mean from beta = C^-1 r
+// mu*(t*_i) = sum_j k(t*_i - t_j) beta_j  (fit.py:6407-6414, 7536-7554; tinygp's zero mean function).  One CTA per
+// sample, one thread per test time, j ascending with a single accumulator (fixed summation order); the covariance
+// function is branch-free, so four of its chains are in flight per thread.  fp64-pipe bound: T * N covariance
+// evaluations per sample, ~16x the factorisation's N^2 / 2.
+__global__ void __launch_bounds__(kThreads)
+gp_mean_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, const double* __restrict__ beta,
+               const double* __restrict__ times, int64_t T_n, double* __restrict__ mean_out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int N = P.n_epochs;
+  double* ts = reinterpret_cast<double*>(smem);
+  double* bs = ts + ((N + 1) & ~1);
+  for (int j = threadIdx.x; j < N; j += blockDim.x) ts[j] = P.epochs[j];
+  for (int64_t s = blockIdx.x; s < S; s += gridDim.x) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < N; j += blockDim.x) bs[j] = beta[s * N + j];
+    const double* row = theta + s * P.ndim;
+    double hp[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = P.src_col[P.n_model + k];
+      hp[k] = c >= 0 ? row[c] : P.src_const[P.n_model + k];
+    }
+    const GpHyper hyp = gp_hyper(hp[0], hp[1], hp[2], hp[3]);
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < T_n; i += blockDim.x) {
+      const double t = times[i];
+      double acc = 0.0;
+#pragma unroll 4
+      for (int j = 0; j < N; ++j) acc = fma(gp_cov(t - ts[j], hyp), bs[j], acc);
+      mean_out[s * T_n + i] = acc;
+    }
+  }
 }
 
 }  // namespace rvlp
