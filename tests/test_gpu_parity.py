@@ -582,3 +582,54 @@ def test_fp64_peak_probe(cuda):
     from ravest_b200 import _lib
     flops, ms = _lib.measure_fp64_peak(0, 2048)
     assert 5e12 < flops < 8e13, flops
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [30, 57, 120, 170])
+def test_gp_pipelined_kernel_is_bit_stable_under_grid_size_and_row_order(cuda, monkeypatch, N):
+    """The software-pipelined K3 (rvlp_gp_pipe.cuh): a sample's bits depend on its own row only - not on how many
+    CTAs share the work (each CTA overlaps ITS consecutive samples, so the neighbours differ with the grid), not on
+    the row order, not on rejected rows sitting in between (they take the barrier-only path)."""
+    from ravest_b200 import workloads
+    spec, theta = workloads.make_c5(n_samples=700, n_planets=1, n_epochs=N, seed=900 + N)
+    names = workloads.free_names(spec) + list(spec["hyperparams"])
+    theta[5::37, names.index("gp_amp")] = -1.0                 # rejected rows between good ones
+    post = _post(spec)
+    th = cuda.as_tensor(theta, device="cuda")
+    base = post.log_probability_batch(th).cpu().numpy()
+    assert np.isneginf(base[5::37]).all() and np.isfinite(base).sum() > 600
+    for cap in ("1", "7", "148"):
+        monkeypatch.setenv("RVLP_GP_GRID", cap)
+        got = post.log_probability_batch(th).cpu().numpy()
+        assert np.array_equal(got.view(np.int64), base.view(np.int64)), cap
+    monkeypatch.delenv("RVLP_GP_GRID")
+    perm = np.random.default_rng(3).permutation(len(theta))
+    got = post.log_probability_batch(cuda.as_tensor(theta[perm], device="cuda")).cpu().numpy()
+    assert np.array_equal(got.view(np.int64), base[perm].view(np.int64))
+    one = post.log_probability_batch(th[11:12]).cpu().numpy()
+    assert one.view(np.int64)[0] == base.view(np.int64)[11]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [3, 30, 57, 120, 170])
+def test_gp_conditioning_pipelined_path_matches_single_kernel(cuda, monkeypatch, N):
+    """Row f-4: the product path (pipelined factorisation with the factor kept in shared memory + blocked back
+    substitution + mean kernel) against the older single kernel (RVLP_GP_KERNEL=smem), both on the GPU, at every
+    tile size incl. the padded last panel (TT does not divide N) - mean, chi^2 and the NaN rows."""
+    from ravest_b200 import workloads
+    spec, theta = workloads.make_c5(n_samples=60, n_planets=1, n_epochs=N, seed=1200 + N)
+    names = workloads.free_names(spec) + list(spec["hyperparams"])
+    theta[7, names.index("gp_period")] = 0.0                   # the reference raises: NaN row
+    post = _post(spec)
+    times = np.linspace(spec["time"].min() - 3.0, spec["time"].max() + 3.0, 77)
+    mean, chi2 = post.ctx.gp_predict(theta, times, want_chi2=True)
+    monkeypatch.setenv("RVLP_GP_KERNEL", "smem")
+    mean0, chi20 = post.ctx.gp_predict(theta, times, want_chi2=True)
+    mean, chi2, mean0, chi20 = (x.cpu().numpy() for x in (mean, chi2, mean0, chi20))
+    assert np.array_equal(np.isnan(mean), np.isnan(mean0)) and np.array_equal(np.isnan(chi2), np.isnan(chi20))
+    assert np.isnan(mean[7]).all() and np.isnan(chi2[7])
+    ok = ~np.isnan(chi2)
+    assert ok.sum() > 40
+    scale = np.maximum(1.0, np.abs(mean0[ok]).max(axis=1, keepdims=True))
+    assert np.all(np.abs(mean[ok] - mean0[ok]) <= 1e-7 * scale)
+    assert np.all(np.abs(chi2[ok] - chi20[ok]) <= 1e-9 * np.abs(chi20[ok]))
