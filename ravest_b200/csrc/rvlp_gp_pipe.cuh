@@ -37,8 +37,9 @@ __device__ __forceinline__ void named_arrive(int id, int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 // barrier ids: 0 = __syncthreads (stage_problem only); 1..4 = panel barriers A / B x sample parity;
-// 5 + r = "record of the next sample is ready" for the consumer warp of role r (1 <= r <= 7)
-constexpr int kBarPanel = 1, kBarReady = 5;
+// 5 + r = "record of the next sample is ready" for the consumer warp of role r (1 <= r <= 7);
+// 13 = "the staged tiles of the last two roles are built" (early roles arrive, the last two roles wait)
+constexpr int kBarPanel = 1, kBarReady = 5, kBarStage = 13;
 #ifndef RVLP_GP_ABLATE
 #define RVLP_GP_ABLATE 0   /* experiments: 1 no diag arithmetic, 2 no TRSM arithmetic, 3 no update, 4 no covariance build */
 #endif
@@ -57,7 +58,7 @@ __device__ unsigned long long g_gp_pipe_timing[64];
 #define PT_FLUSH() do {} while (0)
 #endif
 
-struct GpPipeSmem { int off_rec, off_resid, off_ctl, off_d, off_p, off_part, off_beta, off_tim, pstride, dsize, rsize, total; };
+struct GpPipeSmem { int off_rec, off_resid, off_ctl, off_d, off_p, off_part, off_beta, off_stage, off_tim, pstride, dsize, rsize, total; };
 // pred: the conditioning variant keeps EVERY panel (the whole factor L, tile-packed: panel p holds tile rows p+1 .. nt-1)
 // and every diagonal tile until the sample's back substitution is done, instead of two alternating panel buffers.
 __host__ __device__ inline GpPipeSmem gp_pipe_smem(const DevProblem& P, const SmemLayout& L, int TT, bool pred = false) {
@@ -76,6 +77,8 @@ __host__ __device__ inline GpPipeSmem gp_pipe_smem(const DevProblem& P, const Sm
   G.off_p = o; o += (pred ? nt * (nt - 1) / 2 : 4 * nt) * G.pstride * 8;   // else (sample parity, panel parity) x tile rows
   G.off_part = o; o += 2 * (32 + 192) * 8;            // per parity: alpha.alpha per panel, the pivots (<= 22 * 8)
   G.off_beta = o; o += (pred ? ntc * TT : 0) * 8;
+  o = (o + 15) & ~15;
+  G.off_stage = o; o += (pred ? 0 : 64) * G.pstride * 8;   // tiles of the last two roles, built by the early roles
   G.off_tim = o; o += 8 * 8 * 8;                      // RVLP_GP_TIMING builds: per-warp phase cycle counters
   G.total = o;
   return G;
@@ -133,6 +136,11 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
     if (((Jt * nt - Jt * (Jt - 1) / 2) >> 5) <= role) last_panel = Jt;
   const int fin_tile = ((ntc - 1) * nt - (ntc - 1) * (ntc - 2) / 2) + (IN - (ntc - 1));   // tile (IN, ntc-1)
   const int fin_role = fin_tile >> 5;
+  // Staging (6 or more roles): roles 1 .. n_prod build the tiles of the last two roles for the next sample while those
+  // are still busy with the late panels of the current one; otherwise the last roles' own build would be exposed
+  // (14 % of the sample time, profiles/r01i_gp_phase_timing.md).
+  const bool stage_on = !PRED && nwu >= 6;          // measured: +3 % for K3, -7 % for the conditioning variant (shared memory)
+  const int n_prod = nwu - 3 < 4 ? nwu - 3 : 4;
 
   // ---- producer (warp 0): record, residual, hyperparameter constants and reject flags of sample s2
   auto produce = [&](int64_t s2, int pb) {
@@ -223,45 +231,80 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
     } else {
       GpHyper hyp;
       hyp.inv_P = ctl[0]; hyp.inv_le = ctl[1]; hyp.gamma = ctl[2]; hyp.A2 = ctl[3];
-      double a[TT][TT];                                       // gp.py:145-156, fit.py:8094-8096
-      {
-        // One tile row per trip of a ROLLED loop (TT independent covariance chains in flight), shifted into the
-        // register tile with static indices.  Fully unrolled, the build was 3 000 instructions per thread and -
-        // with the warps of two CTAs in different code regions - instruction-fetch bound (17 k cycles per tile).
-        double tcol[TT];
+      // One row of tile (It, Jt2): TT independent covariance chains (branch-free, rvlp_gpcov.cuh) + the row's fix-ups:
+      // out-of-triangle zeros, white-noise diagonal (fit.py:8094-8096), the residual row N, identity padding beyond
+      // it (so the diagonal-tile code needs no masks).
+      auto tile_row = [&](int It, int Jt2, bool has, int r, double (&row)[TT]) {
+        const int i = It * TT + r, cc0 = Jt2 * TT;
+        const int ic = i < N ? i : N - 1;
+        const double ti = T.t[ic];
+        const bool cov_row = has && i < N;
+        const bool res_row = has && i == N;
+        const double dterm = T.e2[ic] + sr[kHdr + P.n_inst + T.inst[ic]];
 #pragma unroll
-        for (int c = 0; c < TT; ++c) tcol[c] = T.t[c0 + c < N ? c0 + c : N - 1];
+        for (int c = 0; c < TT; ++c) {
+          const double tc = T.t[cc0 + c < N ? cc0 + c : N - 1];
+          row[c] = RVLP_GP_ABLATE == 4 ? ti - tc : gp_cov(ti - tc, hyp);
+        }
+#pragma unroll
+        for (int c = 0; c < TT; ++c) {
+          const int k = cc0 + c;
+          double v = (cov_row && k <= i) ? row[c] : 0.0;
+          if (cov_row && k == i) v += dterm;
+          if (res_row && k < N) v = resid[k];
+          if (has && i >= N && k == i) v = 1.0;
+          row[c] = v;
+        }
+      };
+      double a[TT][TT];                                       // gp.py:145-156, fit.py:8094-8096
+      if (stage_on && role >= nwu - 2) {
+        // the last two roles come out of the previous sample when everybody else is already waiting for them:
+        // their tiles were built by the early roles (below) into shared memory
+        named_sync(kBarStage, (n_prod + 2) * 32);
+        const double2* st = reinterpret_cast<const double2*>(smem + G.off_stage) + (rid - (nwu - 2) * 32) * (PS / 2);
+#pragma unroll
+        for (int r = 0; r < TT; ++r)
+#pragma unroll
+          for (int c = 0; c < TT; c += 2) {
+            const double2 v = st[(r * TT + c) / 2];
+            a[r][c] = v.x; a[r][c + 1] = v.y;
+          }
+      } else {
+        // One tile row per trip of a ROLLED loop, shifted into the register tile with static indices.  Fully unrolled,
+        // the build was 3 000 instructions per thread and - with the warps of two CTAs in different code regions -
+        // instruction-fetch bound (17 k cycles per tile).
 #pragma unroll
         for (int r = 0; r < TT; ++r)
 #pragma unroll
           for (int c = 0; c < TT; ++c) a[r][c] = 0.0;
 #pragma unroll 1
         for (int r = 0; r < TT; ++r) {
-          const int i = r0 + r;
-          const int ic = i < N ? i : N - 1;
-          const double ti = T.t[ic];
-          const bool cov_row = has_tile && i < N;
-          const bool res_row = has_tile && i == N;
-          const double dterm = T.e2[ic] + sr[kHdr + P.n_inst + T.inst[ic]];   // fit.py:8094-8096
           double row[TT];
-#pragma unroll
-          for (int c = 0; c < TT; ++c)
-            row[c] = RVLP_GP_ABLATE == 4 ? ti - tcol[c] : gp_cov(ti - tcol[c], hyp);     // branch-free (rvlp_gpcov.cuh)
-#pragma unroll
-          for (int c = 0; c < TT; ++c) {
-            const int k = c0 + c;
-            double v = (cov_row && k <= i) ? row[c] : 0.0;
-            if (cov_row && k == i) v += dterm;
-            if (res_row && k < N) v = resid[k];
-            if (has_tile && i >= N && k == i) v = 1.0;         // identity padding: the diagonal-tile code needs no masks
-            row[c] = v;
-          }
+          tile_row(I, J, has_tile, r, row);
 #pragma unroll
           for (int q = 0; q + 1 < TT; ++q)
 #pragma unroll
             for (int c = 0; c < TT; ++c) a[q][c] = a[q + 1][c];
 #pragma unroll
           for (int c = 0; c < TT; ++c) a[TT - 1][c] = row[c];
+        }
+        if (stage_on && role >= 1 && role <= n_prod) {
+          // producers: rows of the staged tiles, (tile, row) tasks dealt round-robin to the producer lanes
+          const int n_stage = ntiles - (nwu - 2) * 32;
+          double2* st = reinterpret_cast<double2*>(smem + G.off_stage);
+#pragma unroll 1
+          for (int task = (role - 1) * 32 + lane; task < n_stage * TT; task += n_prod * 32) {
+            const int tl = task / TT, r = task - tl * TT;
+            int J2 = 0, rem2 = (nwu - 2) * 32 + tl;
+            while (rem2 >= nt - J2) { rem2 -= nt - J2; ++J2; }
+            double row[TT];
+            tile_row(J2 + rem2, J2, true, r, row);
+#pragma unroll
+            for (int c = 0; c < TT; c += 2) st[tl * (PS / 2) + (r * TT + c) / 2] = make_double2(row[c], row[c + 1]);
+          }
+          __threadfence_block();
+          __syncwarp();
+          named_arrive(kBarStage, (n_prod + 2) * 32);
         }
       }
       PT_LAP(1);
