@@ -366,6 +366,12 @@ def main() -> None:
                              "samples": len(t2)}
                     if other in FLOPS_PER_UNIT:
                         entry["roofline_frac"] = u2 * FLOPS_PER_UNIT[other] / peak_flops
+                    elif other == "c5":
+                        # ~1.36e6 algorithmic fp64 FLOPs per GP log-prob at N = 120, one planet
+                        # (mean model 4.9e4 + covariance build 7.1e5 + Cholesky N^3/3 5.8e5 + solve / log-det 2e4)
+                        entry["flops_per_logprob"] = 1.36e6
+                        entry["roofline_frac"] = entry["logprob_per_s"] * 1.36e6 / peak_flops
+                        entry["kernel"] = "rvlp::gp_logprob_pipe_kernel<6, false>"
                     others[other] = entry
                     del p2, th2, o2
                 except Exception as ex:       # report, never hide
