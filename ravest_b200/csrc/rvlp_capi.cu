@@ -106,7 +106,7 @@ static K1Shape k1_shape(int v, const DevProblem& P, const SmemLayout& L) {
   s.threads = kThreads;
   s.workers = kWarps;
   s.smem = L.total;
-  s.max_nb = kG;
+  s.max_nb = P.batch_cap > kG ? P.batch_cap : kG;
   if (v == 1) s.fn = ge ? logprob_kernel<2, 3, true> : logprob_kernel<2, 3, false>;
   else s.fn = ge ? logprob_kernel<kW, RVLP_MIN_BLOCKS, true> : logprob_kernel<kW, RVLP_MIN_BLOCKS, false>;
   return s;
@@ -183,6 +183,15 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
   P.n_priors = d->n_priors; P.n_hyper = d->n_hyper; P.n_model = n_model; P.n_epochs = (int)n_epochs;
   P.n_pad = (int)((n_epochs + kPadTo - 1) / kPadTo * kPadTo);   // whole lane groups; x28 B is a multiple of 16 for the bulk copy
   P.t0 = d->t0; P.jacobian = d->jacobian; P.renorm = d->renorm;
+  // samples per prologue batch: enough to fill the 32 lanes of the (sample, planet) phase, 4 .. 16
+  P.batch_cap = P.n_planets > 0 ? 32 / P.n_planets : 16;
+  P.batch_cap = P.batch_cap < kG ? kG : (P.batch_cap > 16 ? 16 : P.batch_cap);
+  if (const char* e = getenv("RVLP_BATCH_CAP")) {            // experiments (tools/variant_time.py)
+    const int v = atoi(e);
+    if (v >= kG && v <= 32) P.batch_cap = v;
+  }
+  P.n_pad = (int)((n_epochs + kPadTo - 1) / kPadTo * kPadTo);
+  while (P.batch_cap > kG && smem_layout(P).total > 74 * 1024) --P.batch_cap;   // keep three CTAs per SM possible
 
   // packed, padded epoch block: [t | vel | velerr^2] doubles + int32 instrument ids
   std::vector<unsigned char> blk((size_t)P.n_pad * 28);
@@ -305,8 +314,10 @@ static int launch_logprob(rvlp_ctx* c, const double* theta, int64_t S, double* o
   int rc = grid_for(c->device, (const void*)kern, smem, INT_MAX, &grid, shape.threads);   // full wave
   if (rc) return rc;
   // samples per prologue batch: kG when every resident worker still gets a batch, else 1 (latency of small S)
+  // (beyond kG only while every warp still gets four or more batches: the dynamic schedule's tail is one batch)
   int64_t per_warp = S / ((int64_t)grid * shape.workers);
-  const int nb = (int)(per_warp >= shape.max_nb ? shape.max_nb : (per_warp < 1 ? 1 : per_warp));
+  int nb = (int)(per_warp >= kG ? kG : (per_warp < 1 ? 1 : per_warp));
+  if (per_warp / 4 > kG) nb = (int)(per_warp / 4 < shape.max_nb ? per_warp / 4 : shape.max_nb);
   const int64_t want = ((S + nb - 1) / nb + shape.workers - 1) / shape.workers;
   if (want < grid) grid = (int)want;
   unsigned long long* tickets = nullptr;

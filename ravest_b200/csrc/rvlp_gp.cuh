@@ -61,7 +61,7 @@ gp_logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, dou
   const int N = P.n_epochs;
 
   for (int64_t s = blockIdx.x; s < S; s += gridDim.x) {
-    if (warp == 0) sample_prologue(P, T, theta, s, s + 1, scratch, rec, lane, true);
+    if (warp == 0) sample_prologue(P, T, theta, s, s + 1, scratch, rec, lane, true, 1, reinterpret_cast<double*>(smem + L.off_pv));
     __syncthreads();
     const double* sr = scratch;
     const int flags = __double2loint(sr[1]);
@@ -208,7 +208,7 @@ gp_logprob_tiled_kernel(DevProblem P, const double* __restrict__ theta, int64_t 
   const int r0 = I * TT, c0 = J * TT;
 
   for (int64_t s = blockIdx.x; s < S; s += gridDim.x) {
-    if (warp == 0) sample_prologue(P, T, theta, s, s + 1, scratch, rec, lane, true);
+    if (warp == 0) sample_prologue(P, T, theta, s, s + 1, scratch, rec, lane, true, 1, reinterpret_cast<double*>(smem + L.off_pv));
     __syncthreads();
     const double* sr = scratch;
     const int flags = __double2loint(sr[1]);
@@ -431,7 +431,7 @@ gp_logprob_blocked_kernel(DevProblem P, const double* __restrict__ theta, int64_
 
   for (int64_t s = blockIdx.x; s < S; s += gridDim.x) {
     GPT_START();
-    if (warp == 0) sample_prologue(P, T, theta, s, s + 1, scratch, rec, lane, true, 1);
+    if (warp == 0) sample_prologue(P, T, theta, s, s + 1, scratch, rec, lane, true, 1, reinterpret_cast<double*>(smem + L.off_pv));
     __syncthreads();
     GPT_LAP(0);
     const double* sr = scratch;
@@ -656,7 +656,7 @@ gp_predict_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, con
   const double qnan = __longlong_as_double(0x7ff8000000000000ll);
 
   for (int64_t s = blockIdx.x; s < S; s += gridDim.x) {
-    if (warp == 0) sample_prologue(P, T, theta, s, s + 1, scratch, rec, lane, false, 1);
+    if (warp == 0) sample_prologue(P, T, theta, s, s + 1, scratch, rec, lane, false, 1, nullptr);
     __syncthreads();
     const double* sr = scratch;
     const int flags = __double2loint(sr[1]);

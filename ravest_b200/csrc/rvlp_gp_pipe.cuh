@@ -147,7 +147,7 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
     double* sr = recs + pb * rec;
     double* resid = resids + pb * G.rsize;
     double* ctl = ctls + pb * 8;
-    sample_prologue(P, T, theta, s2, s2 + 1, sr, rec, lane, !PRED, 1);
+    sample_prologue(P, T, theta, s2, s2 + 1, sr, rec, lane, !PRED, 1, reinterpret_cast<double*>(smem + L.off_pv));
     const int flags = __double2loint(sr[1]);
     int cf = 0;
     if (PRED ? (flags & (F_PLANET | F_HYPER)) : (flags & (F_JIT | F_HYPER | F_PRIOR))) {

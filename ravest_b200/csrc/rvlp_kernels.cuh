@@ -54,6 +54,7 @@ constexpr double kLog2Pi = 1.8378770664093453;   // np.log(2*np.pi), fit.py:3595
 struct DevProblem {
   int n_planets, par, n_inst, ndim, n_priors, n_hyper, n_model, n_epochs, n_pad;
   int epochs_global;   // 1: too many epochs for shared memory - the kernels read them from global memory (L1 / L2)
+  int batch_cap;       // samples a warp can take through the prologue together (>= kG; sizes the per-warp scratch)
   double t0, jacobian, renorm;
   const int32_t* src_col;
   const double* src_const;
@@ -72,7 +73,7 @@ enum { F_JIT = 1, F_PLANET = 2, F_PRIOR = 4, F_HYPER = 8, F_SKIP = 16,
        F_CLS_FULL = 64 }; // every planet 0 < e <= 0.97: pipelined (2 fp32 steps, 4th-order fp64 step)
 
 struct SmemLayout {
-  int off_t, off_v, off_e2, off_inst, off_priors, off_srccol, off_srcconst, off_scratch, total;
+  int off_t, off_v, off_e2, off_inst, off_priors, off_srccol, off_srcconst, off_scratch, off_pv, total;
 };
 
 __host__ __device__ inline SmemLayout smem_layout(const DevProblem& P) {
@@ -88,7 +89,9 @@ __host__ __device__ inline SmemLayout smem_layout(const DevProblem& P) {
   L.off_srcconst = o; o += (P.n_model + P.n_hyper) * 8;
   L.off_srccol = o; o += (P.n_model + P.n_hyper) * 4;
   o = (o + 15) & ~15;
-  L.off_scratch = o; o += kWarps * kG * sample_rec_doubles(P.n_planets, P.n_inst) * 8;
+  const int cap = P.batch_cap > kG ? P.batch_cap : kG;
+  L.off_scratch = o; o += kWarps * cap * sample_rec_doubles(P.n_planets, P.n_inst) * 8;
+  L.off_pv = o; o += kWarps * cap * P.n_priors * 8;       // prior values of a batch, one per (sample, prior)
   L.total = o + 16;   // + mbarrier
   return L;
 }
@@ -215,7 +218,7 @@ __device__ __forceinline__ double model_param(const Tables& T, const double* row
 // Phase B: one lane per sample: jitter check, gamma / jitter^2, priors in order.
 __device__ __forceinline__ void sample_prologue(const DevProblem& P, const Tables& T, const double* theta,
                                                 int64_t s0, int64_t S, double* scratch, int rec, int lane,
-                                                bool with_priors, int nb = kG) {
+                                                bool with_priors, int nb, double* pv) {
   const int npl = P.n_planets;
   for (int task = lane; task < nb * npl; task += 32) {
     const int g = task / npl, k = task - g * npl;
@@ -269,15 +272,36 @@ __device__ __forceinline__ void sample_prologue(const DevProblem& P, const Table
         if (!(fabs(h) <= 1.79769313486231570e308) || h <= 0) flags |= F_HYPER;
       }
     }
+    sr[1] = __hiloint2double(0, flags);
+  }
+  __syncwarp();
+  if (with_priors) {
+    // Priors: one lane per (sample, prior) pair instead of one lane walking a sample's priors one after the other
+    // (29 sequential log-pdfs per lane at config 3 were most of the prologue's instructions), values parked in
+    // shared memory, then summed per sample IN THE REFERENCE'S ORDER (fit.py:3685-3691) - same bits as before.
+    const int np = P.n_priors;
+    for (int task = lane; task < nb * np; task += 32) {
+      const int g = task / np, j = task - g * np;
+      if (s0 + g >= S) continue;
+      const double* row = theta + (s0 + g) * P.ndim;
+      const double* planets = scratch + g * rec + kHdr + 2 * P.n_inst;
+      const rvlp_prior& pr = T.priors[j];
+      double x;
+      if (pr.target == RVLP_TARGET_COLUMN) x = row[pr.index];
+      else x = planets[pr.index * kPlanetRec + 9 + pr.target];   // P K e w tp at [10..14]
+      pv[task] = prior_logpdf(pr, x);
+    }
+    __syncwarp();
+  }
+  if (lane < nb && s0 + lane < S) {
+    const int g = lane;
+    double* sr = scratch + g * rec;
+    int flags = __double2loint(sr[1]);
     double lp = 0.0, lhp = 0.0;
     if (with_priors) {
-      for (int j = 0; j < P.n_priors; ++j) {                // fit.py:3685-3691
-        const rvlp_prior& pr = T.priors[j];
-        double x;
-        if (pr.target == RVLP_TARGET_COLUMN) x = row[pr.index];
-        else x = planets[pr.index * kPlanetRec + 9 + pr.target];   // P K e w tp at [10..14]
-        const double v = prior_logpdf(pr, x);
-        if (pr.is_hyper) lhp += v; else lp += v;
+      for (int j = 0; j < P.n_priors; ++j) {
+        const double v = pv[g * P.n_priors + j];
+        if (T.priors[j].is_hyper) lhp += v; else lp += v;
       }
       // a failed Tc->Tp conversion makes a derived Tp NaN, i.e. lp non-finite: fit.py:3478-3482
       if (!(fabs(lp) <= 1.79769313486231570e308)) flags |= F_PRIOR;
@@ -482,9 +506,12 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
   const Tables T = tables_of<GE>(P, L, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
-  double* scratch = reinterpret_cast<double*>(smem + L.off_scratch) + warp * kG * rec;
-  // nb = samples per prologue batch (1..kG): small launches use 1 so that every warp gets a sample;
-  // the bits of a sample's result do not depend on it.
+  const int cap = P.batch_cap > kG ? P.batch_cap : kG;
+  double* scratch = reinterpret_cast<double*>(smem + L.off_scratch) + warp * cap * rec;
+  double* pv = reinterpret_cast<double*>(smem + L.off_pv) + warp * cap * P.n_priors;
+  // nb = samples per prologue batch (1..batch_cap): small launches use 1 so that every warp gets a sample, large
+  // ones as many as fill the lanes of the (sample, planet) and (sample, prior) phases; the bits of a sample's
+  // result do not depend on it.
   const int64_t n_batches = (S + nb - 1) / nb;
   const int64_t gw = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
 #if RVLP_STAGGER_NS > 0
@@ -503,7 +530,7 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
     } else {
       b += nw;
     }
-    sample_prologue(P, T, theta, s0, S, scratch, rec, lane, true, nb);
+    sample_prologue(P, T, theta, s0, S, scratch, rec, lane, true, nb, pv);
     for (int g = 0; g < nb; ++g) {
       const int64_t s = s0 + g;
       if (s >= S) break;
@@ -577,7 +604,7 @@ rv_matrix_kernel(DevProblem P, const double* __restrict__ theta, int64_t S,
     } else {
       b += nw;
     }
-    sample_prologue(P, T, theta, s0, S, scratch, rec, lane, false);
+    sample_prologue(P, T, theta, s0, S, scratch, rec, lane, false, kG, nullptr);
     for (int g = 0; g < kG; ++g) {
       const int64_t s = s0 + g;
       if (s >= S) break;
@@ -629,7 +656,8 @@ walker_check_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, i
   const int64_t gw = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
   for (int64_t b = gw; b < n_batches; b += nw) {
     const int64_t s0 = b * kG;
-    sample_prologue(P, T, theta, s0, S, scratch, rec, lane, true);
+    sample_prologue(P, T, theta, s0, S, scratch, rec, lane, true, kG,
+                    reinterpret_cast<double*>(smem + L.off_pv) + warp * kG * P.n_priors);
     if (lane < kG && s0 + lane < S) {
       const int64_t s = s0 + lane;
       const double* row = theta + s * P.ndim;
