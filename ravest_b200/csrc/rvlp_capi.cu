@@ -186,6 +186,7 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
   // samples per prologue batch: enough to fill the 32 lanes of the (sample, planet) phase, 4 .. 16
   P.batch_cap = P.n_planets > 0 ? 32 / P.n_planets : 16;
   P.batch_cap = P.batch_cap < kG ? kG : (P.batch_cap > 16 ? 16 : P.batch_cap);
+  if (P.n_hyper) P.batch_cap = kG;   // GP contexts: K3 / K7 keep their own records; shared memory decides their occupancy
   if (const char* e = getenv("RVLP_BATCH_CAP")) {            // experiments (tools/variant_time.py)
     const int v = atoi(e);
     if (v >= kG && v <= 32) P.batch_cap = v;
