@@ -600,10 +600,12 @@ int rvlp_gp_predict_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const
       c->beta_rows = S;
     }
     int grid = 0, rc = RVLP_OK;
+    const char* grid_cap = getenv("RVLP_GP_GRID");        // tests / experiments: cap the grid
 #define RVLP_GP_PRED(TT)                                                                                          \
   case TT:                                                                                                        \
     rc = grid_for(c->device, (const void*)gp_logprob_pipe_kernel<TT, true>, c->smem_gp_pipe_pred, S, &grid);      \
     if (rc) return rc;                                                                                            \
+    if (grid_cap && atoi(grid_cap) > 0 && atoi(grid_cap) < grid) grid = atoi(grid_cap);                           \
     gp_logprob_pipe_kernel<TT, true><<<grid, kThreads, c->smem_gp_pipe_pred, st>>>(c->P, theta_dev, S, chi2_dev, c->d_beta); \
     break;
     switch (c->gp_tile) {

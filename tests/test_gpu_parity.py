@@ -633,3 +633,27 @@ def test_gp_conditioning_pipelined_path_matches_single_kernel(cuda, monkeypatch,
     scale = np.maximum(1.0, np.abs(mean0[ok]).max(axis=1, keepdims=True))
     assert np.all(np.abs(mean[ok] - mean0[ok]) <= 1e-7 * scale)
     assert np.all(np.abs(chi2[ok] - chi20[ok]) <= 1e-9 * np.abs(chi20[ok]))
+
+
+@pytest.mark.gpu
+def test_gp_pipelined_kernels_are_run_to_run_deterministic(cuda, monkeypatch):
+    """A shared-memory race in the named-barrier pipeline (compute-sanitizer is not available on the pool) would show
+    up as run-to-run or grid-to-grid bit differences: ten launches each of K3 and K7 at two grid sizes, bit for bit."""
+    from ravest_b200 import workloads
+    for N in (120, 57):
+        spec, theta = workloads.make_c5(n_samples=1500, n_planets=1, n_epochs=N, seed=77 + N)
+        post = _post(spec)
+        th = cuda.as_tensor(theta, device="cuda")
+        times = np.linspace(spec["time"].min(), spec["time"].max(), 33)
+        ref_lp = ref_mean = ref_chi = None
+        for rep in range(10):
+            if rep % 2:
+                monkeypatch.setenv("RVLP_GP_GRID", "37")
+            else:
+                monkeypatch.delenv("RVLP_GP_GRID", raising=False)
+            lp = post.log_probability_batch(th).cpu().numpy().view(np.int64)
+            mean, chi2 = post.ctx.gp_predict(th, times, want_chi2=True)
+            mean, chi2 = mean.cpu().numpy().view(np.int64), chi2.cpu().numpy().view(np.int64)
+            if ref_lp is None:
+                ref_lp, ref_mean, ref_chi = lp, mean, chi2
+            assert np.array_equal(lp, ref_lp) and np.array_equal(mean, ref_mean) and np.array_equal(chi2, ref_chi), rep
