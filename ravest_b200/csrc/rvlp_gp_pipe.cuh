@@ -16,9 +16,13 @@
 //     Kepler residual (4 epochs per lane in flight), hyperparameter constants, reject flags; each consumer warp waits
 //     for it on its own two-warp barrier (bar.arrive by the producer, bar.sync by the consumer);
 //   * every warp builds its covariance tiles for sample s+1 as soon as it has retired from s; the per-sample
-//     buffers (record, residual, diagonal tile, partial sums) are double-buffered by sample parity;
-//   * the panel buffer rows are padded to TT*TT + 2 doubles: the 128-bit loads of the trailing update are
-//     bank-conflict free (tools/upd_probe.cu: 1800 -> 1370 cycles per update at two warps per SMSP).
+//     buffers are multi-buffered (record / residual / constants x3, partial sums x2);
+//   * every panel and diagonal tile of a sample has its own place in shared memory (the whole factor L, tile-packed,
+//     rows padded to TT*TT + 2 doubles: the 128-bit loads of the trailing update are bank-conflict free,
+//     tools/upd_probe.cu: 1800 -> 1370 cycles per update at two warps per SMSP);
+//   * two-stage pipeline (6+ warps): the last two roles used to hold everybody up at panel 0 of the next sample; now
+//     the early roles run panels 0 .. P*-1 of sample s+1 among themselves while the late roles finish sample s, and
+//     the late roles apply the updates they missed in one go from the retained panels before joining at panel P*.
 // Deterministic: fixed tile ownership, fixed summation order inside a tile, the per-panel partial sums
 // (alpha.alpha, pivot mantissa product, pivot exponent sum) are combined by one warp in a fixed butterfly.
 // out[s] depends on (theta[s], epochs) only.
@@ -37,9 +41,16 @@ __device__ __forceinline__ void named_arrive(int id, int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 // barrier ids: 0 = __syncthreads (stage_problem only); 1..4 = panel barriers A / B x sample parity;
-// 5 + r = "record of the next sample is ready" for the consumer warp of role r (1 <= r <= 7);
-// 13 = "the staged tiles of the last two roles are built" (early roles arrive, the last two roles wait)
-constexpr int kBarPanel = 1, kBarReady = 5, kBarStage = 13;
+// 4 + r = "record of the next sample is ready" for the consumer warp of role r (1 <= r <= 7); in the two-stage
+// pipeline the producer is up to two samples ahead of the last two roles, which therefore get two ids each
+// (10 .. 13, alternating with the sample parity); 14 / 15 = the two hand-shakes of the two-stage pipeline (AD: early
+// roles arrive, late roles wait; CU: the reverse).  Barriers 1 .. 15 are all in use.
+// Experiment kept for the record (off): roles 1 and 2 build the tiles of the busiest role (the one just before the late
+// roles) for the next sample into shared memory.  Bit-identical, but 1.53 -> 1.78 ms at N = 120 on B200.
+#ifndef RVLP_GP_STAGE_BUSY
+#define RVLP_GP_STAGE_BUSY 0
+#endif
+constexpr int kBarPanel = 1, kBarReady = 5, kBarReadyLate = 10, kBarAD = 14, kBarCU = 15;
 #ifndef RVLP_GP_ABLATE
 #define RVLP_GP_ABLATE 0   /* experiments: 1 no diag arithmetic, 2 no TRSM arithmetic, 3 no update, 4 no covariance build */
 #endif
@@ -58,27 +69,29 @@ __device__ unsigned long long g_gp_pipe_timing[64];
 #define PT_FLUSH() do {} while (0)
 #endif
 
-struct GpPipeSmem { int off_rec, off_resid, off_ctl, off_d, off_p, off_part, off_beta, off_stage, off_tim, pstride, dsize, rsize, total; };
-// pred: the conditioning variant keeps EVERY panel (the whole factor L, tile-packed: panel p holds tile rows p+1 .. nt-1)
-// and every diagonal tile until the sample's back substitution is done, instead of two alternating panel buffers.
+struct GpPipeSmem { int off_rec, off_resid, off_ctl, off_d, off_p, off_part, off_beta, off_stage, off_stage_flag, off_tim, pstride, dsize, rsize, total; };
+// Every panel (the whole factor L, tile-packed: panel p holds tile rows p+1 .. nt-1) and every diagonal tile of a sample
+// have their own place in shared memory: the two-stage pipeline lets the late roles catch up on panels published long
+// before, and the conditioning variant (pred) back-substitutes from them.
 __host__ __device__ inline GpPipeSmem gp_pipe_smem(const DevProblem& P, const SmemLayout& L, int TT, bool pred = false) {
   GpPipeSmem G;
   int o = (L.total + 15) & ~15;
   const int nt = (P.n_epochs + 1 + TT - 1) / TT;
   const int ntc = (P.n_epochs + TT - 1) / TT;
   const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
-  G.off_rec = o; o += 2 * rec * 8;
+  G.off_rec = o; o += 3 * rec * 8;                    // record / residual / constants: the producer runs up to two samples ahead
   G.rsize = (P.n_epochs + 2) & ~1;
-  G.off_resid = o; o += 2 * G.rsize * 8;
-  G.off_ctl = o; o += 2 * 8 * 8;                      // per parity: inv_P, inv_le, gamma, A2, flags, pad
+  G.off_resid = o; o += 3 * G.rsize * 8;
+  G.off_ctl = o; o += 3 * 8 * 8;                      // per record slot: inv_P, inv_le, gamma, A2, flags, pad
   G.dsize = (TT * TT + TT + 1) & ~1;
-  G.off_d = o; o += (pred ? ntc : 2) * G.dsize * 8;
+  G.off_d = o; o += ntc * G.dsize * 8;                // every diagonal tile of the sample
   G.pstride = TT * TT + 2;
-  G.off_p = o; o += (pred ? nt * (nt - 1) / 2 : 4 * nt) * G.pstride * 8;   // else (sample parity, panel parity) x tile rows
+  G.off_p = o; o += nt * (nt - 1) / 2 * G.pstride * 8; // every panel: panel p holds tile rows p+1 .. nt-1
   G.off_part = o; o += 2 * (32 + 192) * 8;            // per parity: alpha.alpha per panel, the pivots (<= 22 * 8)
   G.off_beta = o; o += (pred ? ntc * TT : 0) * 8;
   o = (o + 15) & ~15;
-  G.off_stage = o; o += (pred ? 0 : 64) * G.pstride * 8;   // tiles of the last two roles, built by the early roles
+  G.off_stage = o; o += (pred || !RVLP_GP_STAGE_BUSY ? 0 : 32) * G.pstride * 8;   // RVLP_GP_STAGE_BUSY experiment
+  G.off_stage_flag = o; o += 16;
   G.off_tim = o; o += 8 * 8 * 8;                      // RVLP_GP_TIMING builds: per-warp phase cycle counters
   G.total = o;
   return G;
@@ -95,6 +108,7 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = smem_layout(P);
   const GpPipeSmem G = gp_pipe_smem(P, L, TT, PRED);
+  if (threadIdx.x == 0) *reinterpret_cast<int*>(smem + G.off_stage_flag) = 0;   // ordered by stage_problem's barriers
   stage_problem(P, L, smem);                       // the last __syncthreads of the kernel
   const Tables T = tables_of(P, L, smem);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -124,11 +138,9 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
   const bool has_tile = J < nt;
   const int r0 = I * TT, c0 = J * TT;
   const int IN = N / TT, rN = N - IN * TT;       // where the residual row lives
-  const int pbytes = nt * PS * 8;                // one panel buffer
   const int pi_off = G.off_p + I * PS * 8, pj_off = G.off_p + (J < nt ? J : 0) * PS * 8;
   opaque_i32(pi_off);
   opaque_i32(pj_off);
-  opaque_i32(pbytes);
   // A warp takes part in panel Jt while it owns a tile of column >= Jt, i.e. while its last tile index
   // (32 warp + 31) is >= the first tile index of column Jt; both the count and my last panel follow from that.
   int last_panel = -1;
@@ -136,17 +148,36 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
     if (((Jt * nt - Jt * (Jt - 1) / 2) >> 5) <= role) last_panel = Jt;
   const int fin_tile = ((ntc - 1) * nt - (ntc - 1) * (ntc - 2) / 2) + (IN - (ntc - 1));   // tile (IN, ntc-1)
   const int fin_role = fin_tile >> 5;
-  // Staging (6 or more roles): roles 1 .. n_prod build the tiles of the last two roles for the next sample while those
-  // are still busy with the late panels of the current one; otherwise the last roles' own build would be exposed
-  // (14 % of the sample time, profiles/r01i_gp_phase_timing.md).
-  const bool stage_on = !PRED && nwu >= 6;          // measured: +3 % for K3, -7 % for the conditioning variant (shared memory)
-  const int n_prod = nwu - 3 < 4 ? nwu - 3 : 4;
-
+  // Two-stage pipeline (6 or more roles, K3 only).  The last two roles leave a sample when everybody else has been
+  // waiting for them at panel 0 of the next one for ~40 % of the sample time.  With every panel kept in shared memory
+  // the early roles do NOT wait: they run panels 0 .. P*-1 of sample s+1 among themselves (P* = the first tile column
+  // the late roles own a tile of) while the late roles finish sample s; the late roles then build their tiles, apply
+  // the P* updates they missed in one go (no barriers in between) and join at panel P*.  Two hand-shakes: AD ("panels
+  // 0 .. P*-1 of this sample are published") and CU ("the late roles have consumed them": the early roles may overwrite
+  // them with the next sample's).
+  const bool two = !PRED && nwu >= 6;
+  int Pstar = 0;
+  {
+    int rem2 = (nwu - 2) * 32;
+    while (two && rem2 >= nt - Pstar) { rem2 -= nt - Pstar; ++Pstar; }
+  }
+  const bool late = two && role >= nwu - 2;
+  const int ad_first = Pstar > 0 ? ((Pstar - 1) * nt - (Pstar - 1) * (Pstar - 2) / 2) >> 5 : 0;   // first role of panel P*-1
+  const int ad_count = (nwu - 2 - ad_first) * 32 + 64;
+  if (late) named_arrive(kBarCU, nwu * 32);      // nothing to consume before the first sample
+  // In the two-stage pipeline the role just before the late ones (it takes part in panels 0 .. P*) never waits: its
+  // cycle IS the sample time.  Roles 1 and 2, which idle for half of it, build its tiles of the next sample into
+  // shared memory and bump a shared-memory counter the busy role waits on.
+  const int busy_role = nwu - 3;
+  const bool stage_prod = RVLP_GP_STAGE_BUSY && two && (role == 1 || role == 2);
+  const bool stage_cons = RVLP_GP_STAGE_BUSY && two && role == busy_role;
+  int n_staged = 0;
   // ---- producer (warp 0): record, residual, hyperparameter constants and reject flags of sample s2
-  auto produce = [&](int64_t s2, int pb) {
-    double* sr = recs + pb * rec;
-    double* resid = resids + pb * G.rsize;
-    double* ctl = ctls + pb * 8;
+  auto produce = [&](int64_t s2, int itn) {
+    const int slot = itn % 3;
+    double* sr = recs + slot * rec;
+    double* resid = resids + slot * G.rsize;
+    double* ctl = ctls + slot * 8;
     sample_prologue(P, T, theta, s2, s2 + 1, sr, rec, lane, !PRED, 1, reinterpret_cast<double*>(smem + L.off_pv));
     const int flags = __double2loint(sr[1]);
     int cf = 0;
@@ -189,7 +220,8 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
     if (lane == 0) ctl[4] = __hiloint2double(0, cf);
     __threadfence_block();
     __syncwarp();
-    for (int w = 1; w < nwu; ++w) named_arrive(kBarReady + w, 64);
+    for (int w = 1; w < nwu; ++w)
+      named_arrive(two && w >= nwu - 2 ? kBarReadyLate + 2 * (w - (nwu - 2)) + (itn & 1) : kBarReady + w - 1, 64);
   };
 
   const int64_t stride = gridDim.x;
@@ -202,12 +234,13 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
     const int64_t s_next = s + stride;
     if (it >= 0) {
     const int b = it & 1;
-    if (role != 0) named_sync(kBarReady + role, 64);
+    if (role != 0) named_sync(late ? kBarReadyLate + 2 * (role - (nwu - 2)) + b : kBarReady + role - 1, 64);
     PT_LAP(0);
-    const double* sr = recs + b * rec;
-    const double* resid = resids + b * G.rsize;
-    const double* ctl = ctls + b * 8;
-    double* dbuf = dbufs + (PRED ? 0 : b * G.dsize);         // PRED: + Jt * dsize inside the panel loop
+    const int slot = it % 3;
+    const double* sr = recs + slot * rec;
+    const double* resid = resids + slot * G.rsize;
+    const double* ctl = ctls + slot * 8;
+    double* dbuf = dbufs;                                    // + Jt * dsize inside the panel loop
     double* part_q = parts + b * (32 + 192), *part_d = part_q + 32;
     const int barA = kBarPanel + 2 * b, barB = barA + 1;
     const int cf = __double2loint(ctl[4]);
@@ -227,7 +260,18 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
         }
         out[s] = r;
       }
-      named_sync(barA, nwu * 32);                            // keeps the warps within one sample of each other
+      // Keep the warps in step.  Lock-step pipeline: one barrier for everybody.  Two-stage pipeline: the early roles
+      // may be two samples ahead of the late ones, so the panel-barrier ids of this parity can still be in use by the
+      // late roles - a rejected sample goes through the same AD / CU hand-shakes as a factorised one, with empty stages.
+      if (!two) {
+        named_sync(barA, nwu * 32);
+      } else if (late) {
+        named_sync(kBarAD, ad_count);
+        named_arrive(kBarCU, nwu * 32);
+      } else {
+        named_sync(kBarCU, nwu * 32);
+        if (role >= ad_first) named_arrive(kBarAD, ad_count);
+      }
     } else {
       GpHyper hyp;
       hyp.inv_P = ctl[0]; hyp.inv_le = ctl[1]; hyp.gamma = ctl[2]; hyp.A2 = ctl[3];
@@ -257,11 +301,14 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
         }
       };
       double a[TT][TT];                                       // gp.py:145-156, fit.py:8094-8096
-      if (stage_on && role >= nwu - 2) {
-        // the last two roles come out of the previous sample when everybody else is already waiting for them:
-        // their tiles were built by the early roles (below) into shared memory
-        named_sync(kBarStage, (n_prod + 2) * 32);
-        const double2* st = reinterpret_cast<const double2*>(smem + G.off_stage) + (rid - (nwu - 2) * 32) * (PS / 2);
+      if (stage_cons) {
+        // all 15 usable named barriers are taken (barrier 0 with a count raised "illegal instruction" on B200): a
+        // monotonic shared-memory counter, bumped once by each of the two producer warps per staged sample
+        n_staged += 2;
+        while (*reinterpret_cast<volatile int*>(smem + G.off_stage_flag) < n_staged) {}
+        __syncwarp();
+        __threadfence_block();
+        const double2* st = reinterpret_cast<const double2*>(smem + G.off_stage) + lane * (PS / 2);
 #pragma unroll
         for (int r = 0; r < TT; ++r)
 #pragma unroll
@@ -288,34 +335,68 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
 #pragma unroll
           for (int c = 0; c < TT; ++c) a[TT - 1][c] = row[c];
         }
-        if (stage_on && role >= 1 && role <= n_prod) {
-          // producers: rows of the staged tiles, (tile, row) tasks dealt round-robin to the producer lanes
-          const int n_stage = ntiles - (nwu - 2) * 32;
+        if (stage_prod) {
+          // (tile, row) tasks of the busy role's 32 tiles, dealt round-robin to the 64 producer lanes
           double2* st = reinterpret_cast<double2*>(smem + G.off_stage);
 #pragma unroll 1
-          for (int task = (role - 1) * 32 + lane; task < n_stage * TT; task += n_prod * 32) {
+          for (int task = (role - 1) * 32 + lane; task < 32 * TT; task += 64) {
             const int tl = task / TT, r = task - tl * TT;
-            int J2 = 0, rem2 = (nwu - 2) * 32 + tl;
-            while (rem2 >= nt - J2) { rem2 -= nt - J2; ++J2; }
+            int J2 = 0, rem2 = busy_role * 32 + tl;
+            while (J2 < nt && rem2 >= nt - J2) { rem2 -= nt - J2; ++J2; }
             double row[TT];
-            tile_row(J2 + rem2, J2, true, r, row);
+            tile_row(J2 + rem2, J2, J2 < nt, r, row);
 #pragma unroll
             for (int c = 0; c < TT; c += 2) st[tl * (PS / 2) + (r * TT + c) / 2] = make_double2(row[c], row[c + 1]);
           }
           __threadfence_block();
           __syncwarp();
-          named_arrive(kBarStage, (n_prod + 2) * 32);
+          if (lane == 0) atomicAdd(reinterpret_cast<int*>(smem + G.off_stage_flag), 1);
         }
       }
       PT_LAP(1);
+      // a -= P_I P_J^T with the rows I and J of the panel buffer at byte offset `shift` (every lane that has a tile)
+      auto trailing_update = [&](int shift) {
+        const double2* pi = reinterpret_cast<const double2*>(smem + pi_off + shift);
+        const double2* pj = reinterpret_cast<const double2*>(smem + pj_off + shift);
+#pragma unroll
+        for (int k = 0; k < TT; ++k) {
+          double Li[TT], Lk[TT];
+#pragma unroll
+          for (int r = 0; r < TT; r += 2) {
+            const double2 u = pi[(k * TT + r) / 2], w = pj[(k * TT + r) / 2];
+            Li[r] = u.x; Li[r + 1] = u.y;
+            Lk[r] = w.x; Lk[r + 1] = w.y;
+          }
+#pragma unroll
+          for (int r = 0; r < TT; ++r)
+#pragma unroll
+            for (int c = 0; c < TT; ++c) a[r][c] = fma(-Li[r], Lk[c], a[r][c]);
+        }
+      };
       // PRED: the factor of the previous sample stays in shared memory until its back substitution is done
       if (PRED) named_sync(barB, nwu * 32);
-      for (int Jt = 0; Jt <= last_panel; ++Jt) {
-        const int nsync = (nwu - ((Jt * nt - Jt * (Jt - 1) / 2) >> 5)) * 32;
-        if (PRED) dbuf = dbufs + Jt * G.dsize;
-        // byte offset of this panel's buffer relative to row 0 of buffer 0 (pi_off / pj_off address row I / J there).
-        // PRED: panel Jt holds tile rows Jt+1 .. nt-1 packed behind the earlier panels.
-        const int pshift = PRED ? (Jt * (nt - 1) - Jt * (Jt - 1) / 2 - Jt - 1) * PS * 8 : (2 * b + (Jt & 1)) * pbytes;
+      int Jt = 0;
+      if (two) {
+        if (late) {
+          // panels 0 .. P*-1 were done without me: wait until they are all published, apply them in one go
+          named_sync(kBarAD, ad_count);
+#pragma unroll 1
+          for (int p = 0; p < Pstar; ++p)
+            if (has_tile) trailing_update((p * (nt - 1) - p * (p - 1) / 2 - p - 1) * PS * 8);
+          named_arrive(kBarCU, nwu * 32);
+          Jt = Pstar;
+        } else {
+          named_sync(kBarCU, nwu * 32);       // the late roles have consumed the previous sample's panels 0 .. P*-1
+        }
+        PT_LAP(7);                            // late: wait for AD + catch-up; early: wait for CU
+      }
+#pragma unroll 1
+      for (; Jt <= last_panel; ++Jt) {
+        const int nsync = ((two && Jt < Pstar ? nwu - 2 : nwu) - ((Jt * nt - Jt * (Jt - 1) / 2) >> 5)) * 32;
+        dbuf = dbufs + Jt * G.dsize;
+        // byte offset of this panel's buffer relative to row 0 of panel 0 (pi_off / pj_off address row I / J there):
+        // panel Jt holds tile rows Jt+1 .. nt-1 packed behind the earlier panels
+        const int pshift = (Jt * (nt - 1) - Jt * (Jt - 1) / 2 - Jt - 1) * PS * 8;
         // ---- 1. diagonal tile: unblocked Cholesky in registers.  One thread works and the panel waits, so this
         //         is the shortest instruction sequence that does it: the pivots go to shared memory as they are (the
         //         log-determinant is formed once per sample by the finishing warp), padding rows / columns are an
@@ -365,8 +446,8 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
         PT_LAP(2);
         {
           // only the roles that own tiles of column Jt wait for the diagonal tile; everybody else goes straight to
-          // barrier B.  (The panel buffers alternate with the panel parity, so a panel is never overwritten while a
-          // slower warp still reads the previous one.)
+          // barrier B.  (Every panel has its own buffer, so a panel is never overwritten while a slower warp still
+          // reads the previous one.)
           const int t0 = Jt * nt - Jt * (Jt - 1) / 2;
           const int wa = t0 >> 5, wb = (t0 + nt - Jt - 1) >> 5;
           if (role >= wa && role <= wb) {
@@ -410,25 +491,9 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
         }
         named_sync(barB, nsync);
         PT_LAP(4);
+        if (two && Jt == Pstar - 1) named_arrive(kBarAD, ad_count);   // panels 0 .. P*-1 are all published
         // ---- 3. trailing tiles: a -= P_I P_J^T
-        if (has_tile && J > Jt && RVLP_GP_ABLATE != 3) {
-          const double2* pi = reinterpret_cast<const double2*>(smem + pi_off + pshift);
-          const double2* pj = reinterpret_cast<const double2*>(smem + pj_off + pshift);
-#pragma unroll
-          for (int k = 0; k < TT; ++k) {
-            double Li[TT], Lk[TT];
-#pragma unroll
-            for (int r = 0; r < TT; r += 2) {
-              const double2 u = pi[(k * TT + r) / 2], w = pj[(k * TT + r) / 2];
-              Li[r] = u.x; Li[r + 1] = u.y;
-              Lk[r] = w.x; Lk[r + 1] = w.y;
-            }
-#pragma unroll
-            for (int r = 0; r < TT; ++r)
-#pragma unroll
-              for (int c = 0; c < TT; ++c) a[r][c] = fma(-Li[r], Lk[c], a[r][c]);
-          }
-        }
+        if (has_tile && J > Jt && RVLP_GP_ABLATE != 3) trailing_update(pshift);
         PT_LAP(5);
       }
       // ---- the warp that saw the last panel combines the per-panel partial sums (fixed butterfly)
@@ -509,10 +574,10 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
         }
       }
     }
-    PT_LAP(7);
+    PT_LAP(5);
     }
     if (s_next >= S) break;
-    if (role == 0) produce(s_next, (it + 1) & 1);
+    if (role == 0) produce(s_next, it + 1);
     PT_LAP(6);
   }
   PT_FLUSH();

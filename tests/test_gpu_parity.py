@@ -642,6 +642,9 @@ def test_gp_pipelined_kernels_are_run_to_run_deterministic(cuda, monkeypatch):
     from ravest_b200 import workloads
     for N in (120, 57):
         spec, theta = workloads.make_c5(n_samples=1500, n_planets=1, n_epochs=N, seed=77 + N)
+        names = workloads.free_names(spec) + list(spec["hyperparams"])
+        theta[::3, names.index("gp_amp")] = -1.0            # every third row and a burst are rejected: the early warps
+        theta[600:640, names.index("gp_amp")] = -1.0        # run ahead over them (two-stage pipeline hand-shakes)
         post = _post(spec)
         th = cuda.as_tensor(theta, device="cuda")
         times = np.linspace(spec["time"].min(), spec["time"].max(), 33)

@@ -7,7 +7,7 @@ from ravest_b200 import fit, workloads, _lib
 lib = _lib.load()
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 120
 S = int(sys.argv[2]) if len(sys.argv) > 2 else 10000
-names = ["wait record", "build tiles", "diag / idle", "barrier A", "trsm + barrier B", "update", "produce", "final"]
+names = ["wait record", "build tiles", "diag / idle", "barrier A", "trsm + barrier B", "update+final", "produce", "AD+catchup/CU"]
 spec, theta = workloads.make_c5(n_samples=S, n_planets=1, n_epochs=N)
 post = fit.from_spec(spec)
 th = torch.as_tensor(theta, device="cuda"); out = torch.empty(S, dtype=torch.float64, device="cuda")
@@ -27,4 +27,4 @@ for cap in ("0", "148"):
     print(f"N={N} S={S} grid cap {cap}: {ms:.3f} ms  {S / ms * 1e3:.3e} logprob/s; ~{ns / 3:.0f} samples per CTA; cycles per sample:")
     print("   warp " + " ".join(f"{n[:13]:>14s}" for n in names) + f" {'sum':>10s}")
     for w in range(8):
-        print(f"   {w:4d} " + " ".join(f"{v[w, k] / ns:14.0f}" for k in range(8)) + f" {v[w].sum() / ns:10.0f}")
+        print(f"   w{w} r{(7 - w) if w < 4 else (w - 4)} " + " ".join(f"{v[w, k] / ns:14.0f}" for k in range(8)) + f" {v[w].sum() / ns:10.0f}")
