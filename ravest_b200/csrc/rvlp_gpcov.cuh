@@ -83,8 +83,13 @@ RV_HD double gp_sinpi_frac(double u) {
   const double jt = ffma(x, RVG(8), RINT_MAGIC);   // rint(512 x)
   const double jf = jt - RINT_MAGIC;
   const double eb = ffma(jf, RVG(9), x);           // x - j / 512, exact, |eb| <= 2^-10
+#if defined(__CUDA_ARCH__)
+  const unsigned j = (unsigned)lo32(jt) & 0x7ffu;  // rint(512 x) <= 805 in the low bits of the magic sum; u = inf / NaN:
+                                                   // any 11-bit index stays inside the (padded) table, the result is NaN
+#else
   int j = lo32(jt);
-  j = j < 0 ? 0 : (j > kTabN - 1 ? kTabN - 1 : j); // u = inf / NaN: keep the index inside the table (result is NaN anyway)
+  j = j < 0 ? 0 : (j > kTabN - 1 ? kTabN - 1 : j);
+#endif
 #if defined(__CUDA_ARCH__)
   const double2 sc = __ldg(&kSinCosTabDev[j]);
   const double sa = sc.x, ca = sc.y;

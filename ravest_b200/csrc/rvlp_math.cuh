@@ -106,7 +106,7 @@ constexpr int kTabN = 1610;
 #define RVLP_SINCOS_TABLE 1
 #endif
 #if defined(__CUDACC__)
-__device__ double2 kSinCosTabDev[kTabN];
+__device__ double2 kSinCosTabDev[2048];   // kTabN entries used; padded so that an 11-bit index can never leave it
 #endif
 struct SinCosPair { double s, c; };
 inline const SinCosPair* sincos_table_host() {
@@ -220,7 +220,9 @@ RV_HD void sincos_0pi_table(float E0f, double& s, double& c) {
   const float ebf = ffmaf(jf, -0.001953125f, E0f);        // E0 - j / 512, exact
   const double eb = (double)ebf;
 #if defined(__CUDA_ARCH__)
-  const int j = __float_as_int(t) - 0x4b400000;
+  // t = 1.5 * 2^23 + j: j sits in the low mantissa bits.  Masking (instead of subtracting the bias) gives an unsigned
+  // 11-bit index: one LOP3 + one IMAD.WIDE.U32 for the address instead of five 64-bit integer instructions.
+  const unsigned j = (unsigned)__float_as_int(t) & 0x7ffu;
   const double2 sc = __ldg(&kSinCosTabDev[j]);
   const double sa = sc.x, ca = sc.y;
 #else
