@@ -266,7 +266,7 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
 #define RVLP_GP_ATTR(TT)                                                                                                 \
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_pipe_kernel<TT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem)); \
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_pipe_kernel<TT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-    RVLP_GP_ATTR(2) RVLP_GP_ATTR(4) RVLP_GP_ATTR(6) RVLP_GP_ATTR(8)
+    RVLP_GP_ATTR(2) RVLP_GP_ATTR(4) RVLP_GP_ATTR(6) RVLP_GP_ATTR(8) RVLP_GP_ATTR(10)
 #undef RVLP_GP_ATTR
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_blocked_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
@@ -549,7 +549,16 @@ int rvlp_gp_logprob_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
     RVLP_GP_TILED(4)
     RVLP_GP_TILED(6)
     RVLP_GP_TILED(8)
-    default:   // N > 175 epochs: shared-memory right-looking kernel
+    case 10:   // 176 .. 219 epochs: 10 x 10 register tiles exist for the pipelined kernel only
+      if (use_pipe && c->smem_gp_pipe <= c->max_smem) {
+        rc = grid_for(c->device, (const void*)gp_logprob_pipe_kernel<10, false>, c->smem_gp_pipe, S, &grid);
+        if (rc) return rc;
+        if (grid_cap && atoi(grid_cap) > 0 && atoi(grid_cap) < grid) grid = atoi(grid_cap);
+        gp_logprob_pipe_kernel<10, false><<<grid, kThreads, c->smem_gp_pipe, st>>>(c->P, theta_dev, S, out_dev, nullptr);
+        break;
+      }
+      // fall through
+    default:   // more epochs (or RVLP_GP_KERNEL=smem|column|blocked): shared-memory right-looking kernel
       rc = grid_for(c->device, (const void*)gp_logprob_kernel, c->smem_gp, S, &grid);
       if (rc) return rc;
       gp_logprob_kernel<<<grid, kThreads, c->smem_gp, st>>>(c->P, theta_dev, S, out_dev);
@@ -609,7 +618,7 @@ int rvlp_gp_predict_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const
     gp_logprob_pipe_kernel<TT, true><<<grid, kThreads, c->smem_gp_pipe_pred, st>>>(c->P, theta_dev, S, chi2_dev, c->d_beta); \
     break;
     switch (c->gp_tile) {
-      RVLP_GP_PRED(2) RVLP_GP_PRED(4) RVLP_GP_PRED(6) RVLP_GP_PRED(8)
+      RVLP_GP_PRED(2) RVLP_GP_PRED(4) RVLP_GP_PRED(6) RVLP_GP_PRED(8) RVLP_GP_PRED(10)
       default: return fail(RVLP_EUNSUPPORTED, "no GP tile size for %d epochs", N);
     }
 #undef RVLP_GP_PRED

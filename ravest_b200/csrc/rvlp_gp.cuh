@@ -177,8 +177,8 @@ __host__ __device__ inline GpTiledSmem gp_tiled_smem(const DevProblem& P, const 
   return G;
 }
 __host__ __device__ inline int gp_tile_for(int n_epochs) {
-  const int t[4] = {2, 4, 6, 8};
-  for (int i = 0; i < 4; ++i)
+  const int t[5] = {2, 4, 6, 8, 10};       // 10: pipelined kernels only (rvlp_gp_pipe.cuh), N <= 219
+  for (int i = 0; i < 5; ++i)
     if (n_epochs + 1 <= 22 * t[i]) return t[i];
   return 0;
 }

@@ -87,7 +87,7 @@ __host__ __device__ inline GpPipeSmem gp_pipe_smem(const DevProblem& P, const Sm
   G.off_d = o; o += ntc * G.dsize * 8;                // every diagonal tile of the sample
   G.pstride = TT * TT + 2;
   G.off_p = o; o += nt * (nt - 1) / 2 * G.pstride * 8; // every panel: panel p holds tile rows p+1 .. nt-1
-  G.off_part = o; o += 2 * (32 + 192) * 8;            // per parity: alpha.alpha per panel, the pivots (<= 22 * 8)
+  G.off_part = o; o += 2 * (32 + 224) * 8;            // per parity: alpha.alpha per panel, the pivots (<= 22 * 10)
   G.off_beta = o; o += (pred ? ntc * TT : 0) * 8;
   o = (o + 15) & ~15;
   G.off_stage = o; o += (pred || !RVLP_GP_STAGE_BUSY ? 0 : 32) * G.pstride * 8;   // RVLP_GP_STAGE_BUSY experiment
@@ -241,7 +241,7 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
     const double* resid = resids + slot * G.rsize;
     const double* ctl = ctls + slot * 8;
     double* dbuf = dbufs;                                    // + Jt * dsize inside the panel loop
-    double* part_q = parts + b * (32 + 192), *part_d = part_q + 32;
+    double* part_q = parts + b * (32 + 224), *part_d = part_q + 32;
     const int barA = kBarPanel + 2 * b, barB = barA + 1;
     const int cf = __double2loint(ctl[4]);
     if (cf != 0) {

@@ -543,10 +543,10 @@ def test_gp_against_restatement(cuda):
     assert abs(post.log_probability(x) - got[5]) == 0.0
 
 
-@pytest.mark.parametrize("N", [1, 2, 7, 43, 44, 87, 88, 131, 132, 175, 176, 200])
+@pytest.mark.parametrize("N", [1, 2, 7, 43, 44, 87, 88, 131, 132, 175, 176, 200, 219, 220, 228])
 def test_gp_every_tile_size_and_the_smem_kernel(cuda, N, monkeypatch):
-    """Register-tiled Cholesky at each tile size boundary (T = 2/4/6/8), the shared-memory kernel above
-    N = 175, and both kernels against each other at the same N."""
+    """Register-tiled Cholesky at each tile size boundary (T = 2/4/6/8, and 10 for the pipelined kernel up to
+    N = 219), the shared-memory kernel above that, and every kernel variant against the same oracle at the same N."""
     from oracle import oracle_c
     from ravest_b200 import workloads
     spec, theta = workloads.make_c5(n_samples=48, n_planets=1, n_epochs=N, seed=600 + N)
@@ -585,7 +585,7 @@ def test_fp64_peak_probe(cuda):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("N", [30, 57, 120, 170])
+@pytest.mark.parametrize("N", [30, 57, 120, 170, 205])
 def test_gp_pipelined_kernel_is_bit_stable_under_grid_size_and_row_order(cuda, monkeypatch, N):
     """The software-pipelined K3 (rvlp_gp_pipe.cuh): a sample's bits depend on its own row only - not on how many
     CTAs share the work (each CTA overlaps ITS consecutive samples, so the neighbours differ with the grid), not on
@@ -611,7 +611,7 @@ def test_gp_pipelined_kernel_is_bit_stable_under_grid_size_and_row_order(cuda, m
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("N", [3, 30, 57, 120, 170])
+@pytest.mark.parametrize("N", [3, 30, 57, 120, 170, 200, 219])
 def test_gp_conditioning_pipelined_path_matches_single_kernel(cuda, monkeypatch, N):
     """Row f-4: the product path (pipelined factorisation with the factor kept in shared memory + blocked back
     substitution + mean kernel) against the older single kernel (RVLP_GP_KERNEL=smem), both on the GPU, at every
