@@ -185,7 +185,8 @@ int rvlp_gp_logprob_batch(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samp
  * `gp.condition(y = vel - gamma - planets - trend, X_test = times)` -> conditional mean) and
  * GPFitter._compute_gp_chi2 (fit.py:5386-5429).  mean_dev is [S, n_times] row-major (may be NULL with
  * n_times == 0), chi2_dev [S] (may be NULL).  Rows whose planet parameters or hyperparameters are invalid are
- * NaN (the reference raises there).  Requires n_hyper == 4. */
+ * NaN (the reference raises there).  Requires n_hyper == 4.  The context keeps a grow-only device scratch of
+ * n_samples x n_epochs doubles (beta = C^-1 r per sample) between calls; growing it synchronises the stream once. */
 int rvlp_gp_predict_batch(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples,
                           const double* times_dev, int64_t n_times, double* mean_dev,
                           double* chi2_dev, void* stream);
