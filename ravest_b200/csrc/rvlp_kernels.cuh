@@ -651,14 +651,18 @@ walker_check_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, i
   const Tables T = tables_of(P, L, smem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
-  double* scratch = reinterpret_cast<double*>(smem + L.off_scratch) + warp * kG * rec;
-  const int64_t n_batches = (S + kG - 1) / kG;
   const int64_t gw = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
+  // rows per prologue batch: the context's capacity (fills the lanes of the planet / prior phases) when every warp still
+  // gets a couple of batches, else kG
+  const int cap = P.batch_cap > kG ? P.batch_cap : kG;
+  const int nbw = (S + cap - 1) / cap >= 2 * nw ? cap : kG;
+  double* scratch = reinterpret_cast<double*>(smem + L.off_scratch) + warp * cap * rec;
+  const int64_t n_batches = (S + nbw - 1) / nbw;
   for (int64_t b = gw; b < n_batches; b += nw) {
-    const int64_t s0 = b * kG;
-    sample_prologue(P, T, theta, s0, S, scratch, rec, lane, true, kG,
-                    reinterpret_cast<double*>(smem + L.off_pv) + warp * kG * P.n_priors);
-    if (lane < kG && s0 + lane < S) {
+    const int64_t s0 = b * nbw;
+    sample_prologue(P, T, theta, s0, S, scratch, rec, lane, true, nbw,
+                    reinterpret_cast<double*>(smem + L.off_pv) + warp * cap * P.n_priors);
+    if (lane < nbw && s0 + lane < S) {
       const int64_t s = s0 + lane;
       const double* row = theta + s * P.ndim;
       const double* sr = scratch + lane * rec;
