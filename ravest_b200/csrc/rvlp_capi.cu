@@ -625,7 +625,7 @@ int rvlp_gp_predict_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     if (T > 0) {
-      const int smem_mean = 2 * ((N + 1) & ~1) * 8;
+      const int smem_mean = 4 * ((N + 1) & ~1) * 8;
       rc = grid_for(c->device, (const void*)gp_mean_kernel, smem_mean, S, &grid);
       if (rc) return rc;
       gp_mean_kernel<<<grid, kThreads, smem_mean, st>>>(c->P, theta_dev, S, c->d_beta, times_dev, T, mean_dev);

@@ -47,6 +47,15 @@ __device__ __forceinline__ void named_arrive(int id, int nthreads) {
 // roles arrive, late roles wait; CU: the reverse).  Barriers 1 .. 15 are all in use.
 // Experiment kept for the record (off): roles 1 and 2 build the tiles of the busiest role (the one just before the late
 // roles) for the next sample into shared memory.  Bit-identical, but 1.53 -> 1.78 ms at N = 120 on B200.
+// The periodic factor of the covariance from per-epoch phases: sin^2(pi (t_i - t_j) / P) = (1 - cos(b_i - b_j)) / 2 with
+// cos(b_i - b_j) = cos b_i cos b_j + sin b_i sin b_j, b = 2 pi (t - t_ref) / P computed once per (sample, epoch) by the
+// producer warp (N sincospi instead of N^2 / 2 table sines): 19 instead of 34 fp64 instructions per matrix element.
+#ifndef RVLP_GP_FACTORED
+#define RVLP_GP_FACTORED 1
+#endif
+#ifndef RVLP_GP_RESID_W
+#define RVLP_GP_RESID_W 4
+#endif
 #ifndef RVLP_GP_STAGE_BUSY
 #define RVLP_GP_STAGE_BUSY 0
 #endif
@@ -69,7 +78,7 @@ __device__ unsigned long long g_gp_pipe_timing[64];
 #define PT_FLUSH() do {} while (0)
 #endif
 
-struct GpPipeSmem { int off_rec, off_resid, off_ctl, off_d, off_p, off_part, off_beta, off_stage, off_stage_flag, off_tim, pstride, dsize, rsize, total; };
+struct GpPipeSmem { int off_rec, off_resid, off_ctl, off_d, off_p, off_part, off_beta, off_stage, off_stage_flag, off_cs, off_tim, pstride, dsize, rsize, total; };
 // Every panel (the whole factor L, tile-packed: panel p holds tile rows p+1 .. nt-1) and every diagonal tile of a sample
 // have their own place in shared memory: the two-stage pipeline lets the late roles catch up on panels published long
 // before, and the conditioning variant (pred) back-substitutes from them.
@@ -92,6 +101,7 @@ __host__ __device__ inline GpPipeSmem gp_pipe_smem(const DevProblem& P, const Sm
   o = (o + 15) & ~15;
   G.off_stage = o; o += (pred || !RVLP_GP_STAGE_BUSY ? 0 : 32) * G.pstride * 8;   // RVLP_GP_STAGE_BUSY experiment
   G.off_stage_flag = o; o += 16;
+  G.off_cs = o; o += 3 * 2 * G.rsize * 8;             // per record slot: cos / sin of the epochs' phases (RVLP_GP_FACTORED)
   G.off_tim = o; o += 8 * 8 * 8;                      // RVLP_GP_TIMING builds: per-warp phase cycle counters
   G.total = o;
   return G;
@@ -186,17 +196,22 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
     } else {
       int nonfinite = (!PRED && (flags & F_PLANET)) ? 1 : 0; // fit.py:8022-8024
       if (!nonfinite) {
-        for (int base = 0; base < N; base += 128) {          // residual v - mean, fit.py:7994-8043, 8059
-          double tt[4], rv[4];
-          int idx[4];
+        // residual v - mean, fit.py:7994-8043, 8059.  kRW epochs per lane in flight: the producer has slack (it idles for a
+        // third of the sample time), and the Kepler code is instantiated per width - 2 instead of 4 halves the
+        // producer's footprint in the instruction cache, which it shares with the panel loop of the other warps.
+        constexpr int kRW = RVLP_GP_RESID_W;
+#pragma unroll 1
+        for (int base = 0; base < N; base += 32 * kRW) {
+          double tt[kRW], rv[kRW];
+          int idx[kRW];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < kRW; ++j) {
             idx[j] = base + j * 32 + lane;
             tt[j] = T.t[idx[j] < N ? idx[j] : N - 1];
           }
-          model_rv<4>(P, sr, tt, rv, -1, true);
+          model_rv<kRW>(P, sr, tt, rv, -1, true);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int j = 0; j < kRW; ++j) {
             if (idx[j] < N) {
               if (PRED) {
                 resid[idx[j]] = (T.v[idx[j]] - sr[kHdr + T.inst[idx[j]]]) - rv[j];
@@ -215,6 +230,18 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
         const GpHyper h = gp_hyper(model_param(T, row, P.n_model + 0), model_param(T, row, P.n_model + 1),
                                    model_param(T, row, P.n_model + 2), model_param(T, row, P.n_model + 3));
         ctl[0] = h.inv_P; ctl[1] = h.inv_le; ctl[2] = h.gamma; ctl[3] = h.A2;
+      }
+      if (RVLP_GP_FACTORED) {
+        const double* row = theta + s2 * P.ndim;
+        const double inv_P = 1.0 / model_param(T, row, P.n_model + 3);
+        double* cs = reinterpret_cast<double*>(smem + G.off_cs) + slot * 2 * G.rsize;
+        const double t_ref = T.t[0];
+        for (int j = lane; j < N; j += 32) {
+          double sj, cj;
+          sincospi(2.0 * ((T.t[j] - t_ref) * inv_P), &sj, &cj);
+          cs[j] = cj;
+          cs[G.rsize + j] = sj;
+        }
       }
     }
     if (lane == 0) ctl[4] = __hiloint2double(0, cf);
@@ -275,6 +302,9 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
     } else {
       GpHyper hyp;
       hyp.inv_P = ctl[0]; hyp.inv_le = ctl[1]; hyp.gamma = ctl[2]; hyp.A2 = ctl[3];
+      const double g2 = 0.5 * hyp.gamma;
+      const double* cph = reinterpret_cast<const double*>(smem + G.off_cs) + slot * 2 * G.rsize;
+      (void)g2; (void)cph;
       // One row of tile (It, Jt2): TT independent covariance chains (branch-free, rvlp_gpcov.cuh) + the row's fix-ups:
       // out-of-triangle zeros, white-noise diagonal (fit.py:8094-8096), the residual row N, identity padding beyond
       // it (so the diagonal-tile code needs no masks).
@@ -285,11 +315,22 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
         const bool cov_row = has && i < N;
         const bool res_row = has && i == N;
         const double dterm = T.e2[ic] + sr[kHdr + P.n_inst + T.inst[ic]];
+#if RVLP_GP_FACTORED
+        const double ci = cph[ic], si = cph[G.rsize + ic];
+#pragma unroll
+        for (int c = 0; c < TT; ++c) {
+          const int kc = cc0 + c < N ? cc0 + c : N - 1;
+          const double cd = fma(ci, cph[kc], si * cph[G.rsize + kc]);   // cos of the phase difference
+          const double q = (ti - T.t[kc]) * hyp.inv_le;
+          row[c] = gp_exp_scaled(fma(g2, cd, fma(-0.5 * q, q, -g2)), hyp.A2);
+        }
+#else
 #pragma unroll
         for (int c = 0; c < TT; ++c) {
           const double tc = T.t[cc0 + c < N ? cc0 + c : N - 1];
           row[c] = RVLP_GP_ABLATE == 4 ? ti - tc : gp_cov(ti - tc, hyp);
         }
+#endif
 #pragma unroll
         for (int c = 0; c < TT; ++c) {
           const int k = cc0 + c;
@@ -585,20 +626,27 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
 
 // ------------------------------------------------------------------ K7b: conditional mean from beta = C^-1 r
 // mu*(t*_i) = sum_j k(t*_i - t_j) beta_j  (fit.py:6407-6414, 7536-7554; tinygp's zero mean function).  One CTA per
-// sample, one thread per test time, j ascending with a single accumulator (fixed summation order); the covariance
-// function is branch-free, so four of its chains are in flight per thread.  fp64-pipe bound: T * N covariance
-// evaluations per sample, ~16x the factorisation's N^2 / 2.
+// sample, one thread per test time, j ascending with a single accumulator (fixed summation order).  T * N covariance
+// evaluations per sample, ~16x the factorisation's N^2 / 2: fp64-pipe bound, so the periodic factor is split
+//   sin^2(pi (t* - t_j) / P) = (1 - cos(a_i - b_j)) / 2,   cos(a_i - b_j) = cos a_i cos b_j + sin a_i sin b_j,
+// with a_i = 2 pi (t*_i - t_ref) / P and b_j = 2 pi (t_j - t_ref) / P (t_ref = the first epoch): N + T `sincospi`
+// per sample instead of T * N table sines, 19 instead of 34 fp64 instructions per pair.  The exponent's absolute
+// error (= the covariance's relative error) is ~Gamma/2 * 2 pi |t - t_ref| / P * 1e-16, the same order as the direct
+// form's rounding of |tau| / P.
 __global__ void __launch_bounds__(kThreads)
 gp_mean_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, const double* __restrict__ beta,
                const double* __restrict__ times, int64_t T_n, double* __restrict__ mean_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int N = P.n_epochs;
+  const int Np = (N + 1) & ~1;
   double* ts = reinterpret_cast<double*>(smem);
-  double* bs = ts + ((N + 1) & ~1);
+  double* bs = ts + Np;
+  double* cb = bs + Np;
+  double* sb = cb + Np;
   for (int j = threadIdx.x; j < N; j += blockDim.x) ts[j] = P.epochs[j];
+  const double t_ref = P.epochs[0];
   for (int64_t s = blockIdx.x; s < S; s += gridDim.x) {
     __syncthreads();
-    for (int j = threadIdx.x; j < N; j += blockDim.x) bs[j] = beta[s * N + j];
     const double* row = theta + s * P.ndim;
     double hp[4];
 #pragma unroll
@@ -607,12 +655,26 @@ gp_mean_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, const 
       hp[k] = c >= 0 ? row[c] : P.src_const[P.n_model + k];
     }
     const GpHyper hyp = gp_hyper(hp[0], hp[1], hp[2], hp[3]);
+    const double g2 = 0.5 * hyp.gamma;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      bs[j] = beta[s * N + j];
+      double sj, cj;
+      sincospi(2.0 * ((ts[j] - t_ref) * hyp.inv_P), &sj, &cj);
+      cb[j] = cj; sb[j] = sj;
+    }
     __syncthreads();
     for (int64_t i = threadIdx.x; i < T_n; i += blockDim.x) {
       const double t = times[i];
+      double sa, ca;
+      sincospi(2.0 * ((t - t_ref) * hyp.inv_P), &sa, &ca);
       double acc = 0.0;
 #pragma unroll 4
-      for (int j = 0; j < N; ++j) acc = fma(gp_cov(t - ts[j], hyp), bs[j], acc);
+      for (int j = 0; j < N; ++j) {
+        const double cd = fma(ca, cb[j], sa * sb[j]);         // cos(a_i - b_j)
+        const double q = (t - ts[j]) * hyp.inv_le;
+        const double y = fma(g2, cd, fma(-0.5 * q, q, -g2));  // -Gamma sin^2(.) - q^2 / 2
+        acc = fma(gp_exp_scaled(y, hyp.A2), bs[j], acc);
+      }
       mean_out[s * T_n + i] = acc;
     }
   }
