@@ -112,7 +112,9 @@ __host__ __device__ inline GpPipeSmem gp_pipe_smem(const DevProblem& P, const Sm
 // (fit.py:5428-5429, may be null) and beta_out[s, :] = C^-1 r = L^-T alpha for gp_mean_kernel; a sample the reference
 // raises for (invalid planet / hyperparameters) gives NaN rows.
 template <int TT, bool PRED>
-__global__ void __launch_bounds__(kThreads, (TT >= 8 ? 1 : 2))
+// CTAs per SM by tile size: the small tiles need few registers, and a latency-bound kernel wants every sample in flight it
+// can get (2x2 tiles: 4 CTAs at 64 registers, 4x4: 3 at 80, 6x6: 2 at 128, 8x8 / 10x10: 1 at 255)
+__global__ void __launch_bounds__(kThreads, (TT >= 8 ? 1 : (TT == 6 ? 2 : (TT == 4 ? 3 : 4))))
 gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double* __restrict__ out,
                        double* __restrict__ beta_out) {
   extern __shared__ __align__(16) unsigned char smem[];
