@@ -54,7 +54,7 @@ __device__ __forceinline__ void named_arrive(int id, int nthreads) {
 #define RVLP_GP_FACTORED 1
 #endif
 #ifndef RVLP_GP_RESID_W
-#define RVLP_GP_RESID_W 4
+#define RVLP_GP_RESID_W 0   /* 0: one epoch per lane in flight for the small tiles, two otherwise (measured: 4 is 3-7 % slower) */
 #endif
 #ifndef RVLP_GP_STAGE_BUSY
 #define RVLP_GP_STAGE_BUSY 0
@@ -199,9 +199,9 @@ gp_logprob_pipe_kernel(DevProblem P, const double* __restrict__ theta, int64_t S
       int nonfinite = (!PRED && (flags & F_PLANET)) ? 1 : 0; // fit.py:8022-8024
       if (!nonfinite) {
         // residual v - mean, fit.py:7994-8043, 8059.  kRW epochs per lane in flight: the producer has slack (it idles for a
-        // third of the sample time), and the Kepler code is instantiated per width - 2 instead of 4 halves the
-        // producer's footprint in the instruction cache, which it shares with the panel loop of the other warps.
-        constexpr int kRW = RVLP_GP_RESID_W;
+        // third of the sample time), and the Kepler code is instantiated per width - a narrow one keeps the producer's
+        // footprint in the instruction cache small, which it shares with the panel loop of the other warps.
+        constexpr int kRW = RVLP_GP_RESID_W > 0 ? RVLP_GP_RESID_W : (TT <= 4 ? 1 : 2);
 #pragma unroll 1
         for (int base = 0; base < N; base += 32 * kRW) {
           double tt[kRW], rv[kRW];
