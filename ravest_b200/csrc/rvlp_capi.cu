@@ -351,7 +351,9 @@ int rvlp_ctx_autotune(rvlp_ctx* c, const double* theta_dev, int64_t S, int32_t* 
   if (chosen) *chosen = c->k1;
   if (c->P.n_hyper || S < 4096) return RVLP_OK;             // nothing to choose for GP contexts / tiny batches
   DeviceGuard guard(c->device);
-  const int64_t n = S < 65536 ? S : 65536;
+  // the whole batch up to 2^18 rows: the prologue batch size and the number of batches per warp depend on the row count,
+  // so a short prefix can favour the wrong shape (c2 at 1e5 rows flipped between runs with a 65 536-row prefix)
+  const int64_t n = S < 262144 ? S : 262144;
   double* scratch = nullptr;
   CUDA_TRY(cudaMalloc((void**)&scratch, sizeof(double) * (size_t)n));
   cudaEvent_t a, b;
@@ -371,7 +373,7 @@ int rvlp_ctx_autotune(rvlp_ctx* c, const double* theta_dev, int64_t S, int32_t* 
       cudaEventElapsedTime(&ms, a, b);
       if (rep > 0 && ms < tmin) tmin = ms;
     }
-    if (tmin < best) { best = tmin; best_v = v; }
+    if (tmin < (v == 0 ? best : 0.98f * best)) { best = tmin; best_v = v; }   // the alternative shape must win by 2 %
   }
   cudaEventDestroy(a);
   cudaEventDestroy(b);
