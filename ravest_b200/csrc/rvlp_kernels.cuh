@@ -389,7 +389,9 @@ __device__ __forceinline__ void chi_epilogue(const DevProblem& P, const Tables& 
 }
 
 __device__ __forceinline__ double chi_finish(const ChiAcc& a) {
-  double acc = a.chi + ((double)a.cnt * kLog2Pi + fma((double)a.exsum, 0.6931471805599453, log(a.prodm))) + a.slow;
+  // prodm is a product of mantissas in [1, 2): positive and normal unless it overflowed (> 1023 epochs per lane)
+  const double lm = __double2hiint(a.prodm) < 0x7ff00000 ? log_pos_normal(a.prodm) : log(a.prodm);
+  double acc = a.chi + ((double)a.cnt * kLog2Pi + fma((double)a.exsum, 0.6931471805599453, lm)) + a.slow;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   return acc;

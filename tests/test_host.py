@@ -142,6 +142,15 @@ def test_host_compiled_gp_covariance_is_accurate():
     assert res.stdout.strip().endswith("OK"), res.stdout
 
 
+def test_host_compiled_fast_log_is_accurate():
+    """log_pos_normal (the one log per sample and lane that closes the chi^2 / log-det reduction) against logl."""
+    exe = "/tmp/rvlp_log_check"
+    src = os.path.join(ROOT, "tests", "host", "log_check.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-mfma", "-ffp-contract=off", "-o", exe, src, "-lm"], check=True)
+    res = subprocess.run([exe, "1000000"], capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.strip().endswith("OK"), res.stdout
+
+
 def test_shard_bounds_cover_and_align():
     for S in (0, 1, 3, 4, 5, 31, 32, 1000, 100_003):
         for world in (1, 2, 3, 4, 8):
