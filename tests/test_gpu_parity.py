@@ -585,7 +585,7 @@ def test_fp64_peak_probe(cuda):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("N", [30, 57, 120, 170, 205])
+@pytest.mark.parametrize("N", [30, 57, 100, 110, 120, 131, 150, 170, 205])
 def test_gp_pipelined_kernel_is_bit_stable_under_grid_size_and_row_order(cuda, monkeypatch, N):
     """The software-pipelined K3 (rvlp_gp_pipe.cuh): a sample's bits depend on its own row only - not on how many
     CTAs share the work (each CTA overlaps ITS consecutive samples, so the neighbours differ with the grid), not on
