@@ -124,8 +124,9 @@ void rvlp_ctx_destroy(rvlp_ctx* ctx);
 int rvlp_logprob_batch(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples,
                        double* out_dev, void* stream);
 
-/* Optional, synchronous: times the compiled shapes of the log-probability kernel on (a prefix of) the caller's
- * rows and keeps the fastest for this context; *chosen (may be NULL) gets its index.  The choice changes the
+/* Optional, synchronous: times the compiled shapes of the log-probability kernel on (up to 2^18 of) the caller's
+ * rows and keeps the fastest for this context (the alternative shape must win by 2 %); *chosen (may be NULL) gets its
+ * index.  The choice changes the
  * speed only - every shape produces identical bits (tests/test_gpu_parity.py). */
 int rvlp_ctx_autotune(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples, int32_t* chosen);
 

@@ -281,7 +281,7 @@ class Context:
             out_np = np.empty(th.shape[0], dtype=np.float64)
         if (self.k1_variant is None and th.shape[0] >= self.AUTOTUNE_MIN_ROWS and not self.desc.is_gp
                 and os.environ.get("RVLP_AUTOTUNE", "1") != "0"):
-            self.autotune(th[:1 << 16])
+            self.autotune(th[:1 << 18])
         check(self._lib.rvlp_logprob_batch_host(self._h, th.ctypes.data, th.shape[0], out_np.ctypes.data))
         return out_np
 
