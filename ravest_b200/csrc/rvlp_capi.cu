@@ -423,38 +423,58 @@ int rvlp_logprob_batch_host(rvlp_ctx* c, const double* theta_host, int64_t S, do
   double* dst = out_pinned ? out_host : c->h_out;
   // chunked, chunks alternating between two streams: the H2D of chunk i+1 (and the staging memcpy) overlaps
   // the kernel of chunk i, the D2H of chunk i overlaps the kernel of chunk i+1
-  // Growing chunks (1/16, 1/16, 1/8, 1/4, 1/2 of the rows): the first copy that nothing can hide is small, every
-  // later copy is shorter than the kernel it hides behind, and few launches mean few tails.
+  // Growing chunks (1/64, 1/64, 1/32, 1/16, 1/8, 1/4, 1/2 of the rows): the first staging copy + H2D that nothing can
+  // hide is small (3.6 MB at config 3), every later copy is shorter than the kernel it hides behind, and few launches
+  // mean few tails.  Results are copied back to a pageable caller buffer chunk by chunk as the chunks finish, so only
+  // the last chunk's copy is exposed.
   int64_t bounds[8];
   int nchunks = 0;
   if (S > (1 << 16)) {
-    const int64_t unit = ((S + 15) / 16 + 3) & ~(int64_t)3;
-    const int mult[5] = {1, 1, 2, 4, 8};
+    const int64_t unit = ((S + 63) / 64 + 3) & ~(int64_t)3;
+    const int mult[7] = {1, 1, 2, 4, 8, 16, 32};
     int64_t at = 0;
-    for (int i = 0; i < 5 && at < S; ++i) {
+    for (int i = 0; i < 7 && at < S; ++i) {
       at += unit * mult[i];
-      bounds[nchunks++] = at < S && i < 4 ? at : S;
+      bounds[nchunks++] = at < S && i < 6 ? at : S;
     }
   } else {
     bounds[nchunks++] = S;
   }
+  cudaEvent_t done[8];
+  for (int i = 0; i < nchunks; ++i) CUDA_TRY(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
   int64_t s0 = 0;
-  for (int ci = 0; ci < nchunks; s0 = bounds[ci], ++ci) {
+  int rc = RVLP_OK;
+  for (int ci = 0; ci < nchunks && rc == RVLP_OK; s0 = bounds[ci], ++ci) {
     cudaStream_t st = (ci & 1) ? c->stream2 : c->stream;
     const int64_t n = bounds[ci] - s0;
     const size_t off = (size_t)s0 * (size_t)c->P.ndim;
     const size_t nbytes = sizeof(double) * (size_t)n * (size_t)c->P.ndim;
     if (!in_pinned) memcpy(c->h_theta + off, theta_host + off, nbytes);
-    CUDA_TRY(cudaMemcpyAsync(c->d_theta + off, src + off, nbytes, cudaMemcpyHostToDevice, st));
-    int rc = c->P.n_hyper ? rvlp_gp_logprob_batch(c, c->d_theta + off, n, c->d_out + s0, st)
-                          : launch_logprob(c, c->d_theta + off, n, c->d_out + s0, nullptr, nullptr, st);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(dst + s0, c->d_out + s0, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (cudaMemcpyAsync(c->d_theta + off, src + off, nbytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+      rc = fail(RVLP_ECUDA, "H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    rc = c->P.n_hyper ? rvlp_gp_logprob_batch(c, c->d_theta + off, n, c->d_out + s0, st)
+                      : launch_logprob(c, c->d_theta + off, n, c->d_out + s0, nullptr, nullptr, st);
+    if (rc) break;
+    if (cudaMemcpyAsync(dst + s0, c->d_out + s0, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaEventRecord(done[ci], st) != cudaSuccess)
+      rc = fail(RVLP_ECUDA, "D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream2));
-  if (!out_pinned) memcpy(out_host, c->h_out, sizeof(double) * (size_t)S);
-  return RVLP_OK;
+  if (rc == RVLP_OK) {
+    s0 = 0;
+    for (int ci = 0; ci < nchunks; s0 = bounds[ci], ++ci) {
+      if (cudaEventSynchronize(done[ci]) != cudaSuccess) {
+        rc = fail(RVLP_ECUDA, "batch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        break;
+      }
+      if (!out_pinned) memcpy(out_host + s0, c->h_out + s0, sizeof(double) * (size_t)(bounds[ci] - s0));
+    }
+  }
+  cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->stream2);
+  for (int i = 0; i < nchunks; ++i) cudaEventDestroy(done[i]);
+  return rc;
 }
 
 int rvlp_rv_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const double* times_dev, int64_t T,
