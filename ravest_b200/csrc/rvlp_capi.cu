@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rvlp_bands.cuh"
@@ -394,6 +395,31 @@ int rvlp_logprob_parts_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, do
   return launch_logprob(c, theta_dev, S, nullptr, ll_dev, lp_dev, (cudaStream_t)stream);
 }
 
+// Pageable -> pinned staging copy.  One thread moves ~8 GB/s, which made the NumPy-in path copy-bound (33 ms against a
+// 24 ms kernel at config 3): large chunks are split over up to four threads.
+static void staged_copy(double* dst, const double* src, size_t nbytes) {
+  const size_t kMinPerThread = (size_t)4 << 20;   // 1 MB per thread was slower below ~10 MB payloads (thread start-up)
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nt = nbytes / kMinPerThread;
+  if (nt > 4) nt = 4;
+  if (hw > 0 && nt > hw) nt = hw;
+  if (nt < 2) { memcpy(dst, src, nbytes); return; }
+  const size_t per = ((nbytes / nt) + 63) & ~(size_t)63;
+  std::thread th[3];
+  size_t started = 0;
+  for (size_t i = 1; i < nt; ++i) {
+    const size_t b = i * per, e = (i + 1 == nt) ? nbytes : (i + 1) * per;
+    try {
+      th[started] = std::thread([=] { memcpy((char*)dst + b, (const char*)src + b, e - b); });
+      ++started;
+    } catch (...) {                                   // no thread to be had: copy this slice here
+      memcpy((char*)dst + b, (const char*)src + b, e - b);
+    }
+  }
+  memcpy(dst, src, per < nbytes ? per : nbytes);
+  for (size_t i = 0; i < started; ++i) th[i].join();
+}
+
 int rvlp_logprob_batch_host(rvlp_ctx* c, const double* theta_host, int64_t S, double* out_host) {
   if (!c || S < 0 || (S > 0 && (!theta_host || !out_host))) return fail(RVLP_EINVAL, "bad arguments");
   if (S == 0) return RVLP_OK;
@@ -429,13 +455,20 @@ int rvlp_logprob_batch_host(rvlp_ctx* c, const double* theta_host, int64_t S, do
   // the last chunk's copy is exposed.
   int64_t bounds[8];
   int nchunks = 0;
-  if (S > (1 << 16)) {
-    const int64_t unit = ((S + 63) / 64 + 3) & ~(int64_t)3;
-    const int mult[7] = {1, 1, 2, 4, 8, 16, 32};
+  // number of chunks by payload: 7 from 64 MB, fewer below (a chunk under ~1 MB costs more in launches than it hides)
+  const size_t total_bytes = sizeof(double) * (size_t)S * (size_t)c->P.ndim;
+  int want_chunks = total_bytes >= ((size_t)64 << 20) ? 7 : total_bytes >= ((size_t)16 << 20) ? 5 : total_bytes >= ((size_t)4 << 20) ? 3 : 1;
+  if (const char* e = getenv("RVLP_HOST_CHUNKS")) {         // experiments
+    const int v = atoi(e);
+    if (v >= 1 && v <= 7) want_chunks = v;
+  }
+  if (S > 4096 && want_chunks > 1) {
+    const int64_t parts = (int64_t)1 << (want_chunks - 1);   // 1, 1, 2, 4, ... units
+    const int64_t unit = ((S + parts - 1) / parts + 3) & ~(int64_t)3;
     int64_t at = 0;
-    for (int i = 0; i < 7 && at < S; ++i) {
-      at += unit * mult[i];
-      bounds[nchunks++] = at < S && i < 6 ? at : S;
+    for (int i = 0; i < want_chunks && at < S; ++i) {
+      at += unit * (i == 0 ? 1 : ((int64_t)1 << (i - 1)));
+      bounds[nchunks++] = at < S && i < want_chunks - 1 ? at : S;
     }
   } else {
     bounds[nchunks++] = S;
@@ -449,7 +482,7 @@ int rvlp_logprob_batch_host(rvlp_ctx* c, const double* theta_host, int64_t S, do
     const int64_t n = bounds[ci] - s0;
     const size_t off = (size_t)s0 * (size_t)c->P.ndim;
     const size_t nbytes = sizeof(double) * (size_t)n * (size_t)c->P.ndim;
-    if (!in_pinned) memcpy(c->h_theta + off, theta_host + off, nbytes);
+    if (!in_pinned) staged_copy(c->h_theta + off, theta_host + off, nbytes);
     if (cudaMemcpyAsync(c->d_theta + off, src + off, nbytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
       rc = fail(RVLP_ECUDA, "H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
       break;
