@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY.  Nothing in the product path (`ravest_b200/`), `bench.py`,
 `__graft_entry__.smoke()` or the `-m gpu` tests imports this module: `/root/reference`
-does not exist on the GPU box.  It is used by `tests/golden/make_golden.py` (run in the
+does not exist on the GPU box; the git-ignored installed copy `oracle/_ref/` (oracle/make_ref.py) does travel, and
+is what `bench.py --impl reference` / the `cpu_baseline` leg and the live-reference tests import there.  It is used by `tests/golden/make_golden.py` (run in the
 build container) to produce the committed fixtures, and by a handful of `not gpu` tests that
 are skipped when `/root/reference` is absent.
 
@@ -18,11 +19,24 @@ import os
 import sys
 import types
 
-REFERENCE_SRC = "/root/reference/src"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# 1. the read-only reference tree (build container only); 2. oracle/_ref, the git-ignored installed copy that
+# oracle/make_ref.py (run by __graft_entry__.build()) makes so that the unmodified reference travels to the GPU box
+CANDIDATES = ["/root/reference/src", os.path.join(_HERE, "_ref")]
+
+
+def reference_src() -> str | None:
+    for c in CANDIDATES:
+        if os.path.isfile(os.path.join(c, "ravest", "fit.py")):
+            return c
+    return None
+
+
+REFERENCE_SRC = reference_src() or CANDIDATES[0]
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_SRC, "ravest"))
+    return reference_src() is not None
 
 
 def _stub(name: str, **attrs) -> types.ModuleType:
@@ -35,7 +49,7 @@ def _stub(name: str, **attrs) -> types.ModuleType:
 def import_reference():
     """Return the reference's (model, param, prior, fit) modules, imported unmodified."""
     if not reference_available():
-        raise RuntimeError("reference tree /root/reference is not present on this machine")
+        raise RuntimeError("the reference is not present on this machine (neither /root/reference nor oracle/_ref)")
     if "ravest.fit" in sys.modules and getattr(sys.modules["ravest"], "_is_reference", False):
         r = sys.modules
         return r["ravest.model"], r["ravest.param"], r["ravest.prior"], r["ravest.fit"]
@@ -76,7 +90,7 @@ def import_reference():
         sys.modules["tinygp.kernels"].Kernel = _Anything
 
     pkg = types.ModuleType("ravest")
-    pkg.__path__ = [os.path.join(REFERENCE_SRC, "ravest")]
+    pkg.__path__ = [os.path.join(reference_src(), "ravest")]
     pkg._is_reference = True
     sys.modules["ravest"] = pkg
     model = importlib.import_module("ravest.model")

@@ -88,6 +88,7 @@ class _DeviceBacked:
     """Lazy, picklable ownership of an rvlp context."""
 
     _ctx = None
+    device = None          # None = torch's current device at first use
 
     def _make_descriptor(self) -> Descriptor:
         raise NotImplementedError
@@ -97,7 +98,7 @@ class _DeviceBacked:
         if self._ctx is None:
             self._desc = self._make_descriptor()
             idx = instrument_indices(self.instrument, self.unique_instruments)
-            self._ctx = _lib.Context(self._desc, self.time, self.vel, self.velerr, idx)
+            self._ctx = _lib.Context(self._desc, self.time, self.vel, self.velerr, idx, device=self.device)
         return self._ctx
 
     def __getstate__(self):
