@@ -4,7 +4,7 @@ Run in the build container only (needs /root/reference):
 
     python tests/golden/make_golden.py
 
-Writes tests/golden/{rv,tctp,priors,known_answers,logprob_cases,rv_matrix}.json.
+Writes tests/golden/{rv,tctp,priors,known_answers,logprob_cases,rv_matrix,sample_matrices,c3_c4_subsample}.json.
 Every number in those files is an output of the reference's own code
 (`ravest.model.Planet.radial_velocity`, `Parameterisation.convert_*`, `ravest.prior.*`,
 `ravest.fit.LogPosterior.log_probability`, `Fitter.find_map_estimate`,
@@ -498,6 +498,34 @@ def make_sample_matrices():
     dump("sample_matrices.json", out)
 
 
+def make_full_size_subsamples():
+    """BASELINE configs 2, 3 and 4 at their FULL sizes: a seeded subsample of rows evaluated by the reference itself
+    (`ravest.fit.LogPosterior.log_probability`, one dict per row).  The rows are identified by index into the seeded
+    generator's output (ravest_b200/workloads.py) plus a checksum of the bytes, so the fixture stays small and the
+    GPU tests compare the CUDA path with REFERENCE outputs on those exact configs without going through the product's
+    descriptor compiler or the C restatement."""
+    import hashlib
+    out = []
+    for name, maker, S, n_rows, seed in (("c2", workloads.make_c2, 100_000, 400, 21), ("c3", workloads.make_c3, 1_000_000, 400, 22),
+                                         ("c4", workloads.make_c4, 1_000_000, 400, 23)):
+        spec, theta = maker(S)
+        idx = np.sort(np.random.default_rng(seed).choice(S, n_rows, replace=False))
+        _, lp = ref_logposterior(spec, check_priors=False)
+        names = lp.free_params_names
+        assert names == workloads.free_names(spec)
+        rows = theta[idx]
+        logp = ref_logprob_rows(lp, names, rows)
+        ll = []
+        for r in rows:       # LogLikelihood.__call__ on the full parameter dict (fit.py:3600-3660); -inf for an invalid planet
+            d = lp.fixed_params | dict(zip(names, (float(x) for x in r)))
+            ll.append(float(lp.log_likelihood(d)))
+        out.append({"config": name, "maker": maker.__name__, "n_samples": S, "index": idx, "logprob": logp, "loglike": ll,
+                    "rows_sha256": hashlib.sha256(np.ascontiguousarray(rows).tobytes()).hexdigest(),
+                    "n_epochs": len(spec["time"]), "n_planets": len(spec["planet_letters"])})
+        print(name, "finite", int(np.isfinite(logp).sum()), "of", n_rows)
+    dump("c3_c4_subsample.json", out)
+
+
 if __name__ == "__main__":
     import logging
     logging.disable(logging.CRITICAL)
@@ -508,3 +536,4 @@ if __name__ == "__main__":
     make_logprob_cases()
     make_rv_matrix()
     make_sample_matrices()
+    make_full_size_subsamples()

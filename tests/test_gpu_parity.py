@@ -423,6 +423,7 @@ def test_full_size_c3_properties(cuda):
     idx = np.random.default_rng(0).choice(len(theta), 1500, replace=False)
     ref = oracle_c.OracleProblem(spec).logprob(theta[idx])
     assert_logp_close(out[idx], ref, "c3 subsample")
+    _check_reference_subsample("c3", spec, theta, out, post)      # REFERENCE outputs on this exact config, no shared code
     # the likelihood is invariant under relabelling the planets (same physical model)
     names = post.free_params_names
     swap = theta[idx].copy()
@@ -436,14 +437,52 @@ def test_full_size_c3_properties(cuda):
     assert np.abs(a[ok] - b[ok]).max() <= 1e-9 * np.abs(a[ok]).max()
 
 
+def _check_reference_subsample(config, spec, theta, out, post):
+    """tests/golden/c3_c4_subsample.json: rows of the full-size workload evaluated by the unmodified reference
+    (make_golden.py:make_full_size_subsamples) - independent of the product's descriptor compiler and of oracle.c -
+    plus 200 of them through the dict-level numpy restatement (oracle_py.Problem, no product Descriptor)."""
+    import hashlib
+    from oracle import oracle_py
+    fx = [c for c in load_golden("c3_c4_subsample") if c["config"] == config][0]
+    assert fx["n_samples"] == len(theta)
+    idx = np.asarray(fx["index"])
+    rows = np.ascontiguousarray(theta[idx])
+    assert hashlib.sha256(rows.tobytes()).hexdigest() == fx["rows_sha256"], "workload generator drifted from the fixture"
+    ref = np.asarray(fx["logprob"], dtype=np.float64)
+    assert_logp_close(out[idx], ref, f"{config} vs reference-generated subsample")
+    ll, _ = post.log_probability_parts_batch(rows)
+    assert_logp_close(ll.cpu().numpy(), np.asarray(fx["loglike"], dtype=np.float64), f"{config} log-likelihood vs reference")
+    fin = np.isfinite(ref)
+    err = np.abs(out[idx][fin] - ref[fin])
+    print(f"[measured] {config}: max |dlogp| vs reference = {err.max():.3e} over {int(fin.sum())} rows "
+          f"(max |logp| = {np.abs(ref[fin]).max():.3e})")
+    # the north_star's bare absolute bound holds on every row whose |logp| leaves room for it (ulp(|logp|) << 1e-7)
+    small = np.abs(ref[fin]) < 1e6
+    assert np.all(err[small] <= 1e-7)
+    pr = oracle_py.Problem(spec)
+    sub = slice(0, 200)
+    py = pr.log_probability_batch(rows[sub])
+    assert np.array_equal(py, ref[sub], equal_nan=True), "oracle_py is no longer bit-identical to the reference"
+
+
+
 def test_full_size_c4_high_e(cuda):
     from oracle import oracle_c
     from ravest_b200 import workloads
-    spec, theta = workloads.make_c4(n_samples=200_000)
+    spec, theta = workloads.make_c4(n_samples=1_000_000)
     post = _post(spec)
     out = post.log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
     idx = np.random.default_rng(1).choice(len(theta), 1500, replace=False)
     assert_logp_close(out[idx], oracle_c.OracleProblem(spec).logprob(theta[idx]), "c4 subsample")
+    _check_reference_subsample("c4", spec, theta, out, post)
+
+
+def test_full_size_c2_against_reference_subsample(cuda):
+    from ravest_b200 import workloads
+    spec, theta = workloads.make_c2(n_samples=100_000)
+    post = _post(spec)
+    out = post.log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
+    _check_reference_subsample("c2", spec, theta, out, post)
 
 
 # ------------------------------------------------------------------ shapes, edges, plumbing
@@ -543,6 +582,38 @@ def test_gp_against_restatement(cuda):
     assert abs(post.log_probability(x) - got[5]) == 0.0
 
 
+def test_gp_against_sklearn_fixtures(cuda):
+    """Rows a17, a18, f-4 against an implementation the builder did not write: tests/golden/gp_sklearn.json holds
+    scikit-learn's log marginal likelihood, conditional mean and y^T C^-1 y for the same kernel
+    (tests/golden/make_gp_sklearn.py).  Log-probability to the north_star's 1e-7 absolute (+ 1e-11 relative for the
+    conditioning of the solve), mean to 1e-8 of its scale, chi^2 to 1e-9 relative."""
+    from ravest_b200 import workloads
+    g = load_golden("gp_sklearn")
+    n = 0
+    for c in g["cases"]:
+        spec, theta = workloads.make_c5(n_samples=c["n_samples"], n_planets=c["n_planets"], n_epochs=c["n_epochs"],
+                                        seed=c["seed"])
+        assert np.array_equal(theta, np.asarray(c["theta"]))
+        post = _post(spec)
+        got = post.log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
+        ref = np.asarray(c["logprob"], dtype=np.float64)
+        assert np.array_equal(np.isneginf(got), np.isneginf(ref)), c["name"]
+        fin = np.isfinite(ref)
+        err = np.abs(got[fin] - ref[fin])
+        assert np.all(err <= 1e-7 + 1e-11 * np.abs(ref[fin])), (c["name"], err.max())
+        mean, chi2 = post.ctx.gp_predict(theta, np.asarray(c["times"]), want_chi2=True)
+        mean, chi2 = mean.cpu().numpy(), chi2.cpu().numpy()
+        for i in range(len(theta)):
+            if c["ll"][i] is None:
+                continue
+            mu = np.asarray(c["mean"][i])
+            assert np.abs(mean[i] - mu).max() <= 1e-8 * max(1.0, np.abs(mu).max()), (c["name"], i)
+            assert abs(chi2[i] - c["chi2"][i]) <= 1e-9 * max(1.0, c["chi2"][i]), (c["name"], i)
+            n += 1
+        print(f"[measured] {c['name']}: max |dlogp| vs scikit-learn = {err.max():.3e}")
+    assert n >= 80
+
+
 @pytest.mark.parametrize("N", [1, 2, 7, 43, 44, 87, 88, 131, 132, 175, 176, 200, 219, 220, 228])
 def test_gp_every_tile_size_and_the_smem_kernel(cuda, N, monkeypatch):
     """Register-tiled Cholesky at each tile size boundary (T = 2/4/6/8, and 10 for the pipelined kernel up to
@@ -612,27 +683,32 @@ def test_gp_pipelined_kernel_is_bit_stable_under_grid_size_and_row_order(cuda, m
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("N", [3, 30, 57, 120, 170, 200, 219])
-def test_gp_conditioning_pipelined_path_matches_single_kernel(cuda, monkeypatch, N):
+def test_gp_conditioning_pipelined_path_at_every_tile_size(cuda, N):
     """Row f-4: the product path (pipelined factorisation with the factor kept in shared memory + blocked back
-    substitution + mean kernel) against the older single kernel (RVLP_GP_KERNEL=smem), both on the GPU, at every
-    tile size incl. the padded last panel (TT does not divide N) - mean, chi^2 and the NaN rows."""
+    substitution + mean kernel) at every tile size incl. the padded last panel (TT does not divide N) - mean, chi^2
+    and the NaN rows - against the numpy restatement `oracle_py.Problem.gp_predict`, which
+    tests/test_oracle.py::test_gp_restatement_against_sklearn pins to scikit-learn."""
+    from oracle import oracle_py
     from ravest_b200 import workloads
     spec, theta = workloads.make_c5(n_samples=60, n_planets=1, n_epochs=N, seed=1200 + N)
     names = workloads.free_names(spec) + list(spec["hyperparams"])
     theta[7, names.index("gp_period")] = 0.0                   # the reference raises: NaN row
     post = _post(spec)
+    pr = oracle_py.Problem(spec)
     times = np.linspace(spec["time"].min() - 3.0, spec["time"].max() + 3.0, 77)
     mean, chi2 = post.ctx.gp_predict(theta, times, want_chi2=True)
-    monkeypatch.setenv("RVLP_GP_KERNEL", "smem")
-    mean0, chi20 = post.ctx.gp_predict(theta, times, want_chi2=True)
-    mean, chi2, mean0, chi20 = (x.cpu().numpy() for x in (mean, chi2, mean0, chi20))
-    assert np.array_equal(np.isnan(mean), np.isnan(mean0)) and np.array_equal(np.isnan(chi2), np.isnan(chi20))
+    mean, chi2 = mean.cpu().numpy(), chi2.cpu().numpy()
+    full = pr.gp_log_probability_batch(theta)
     assert np.isnan(mean[7]).all() and np.isnan(chi2[7])
-    ok = ~np.isnan(chi2)
-    assert ok.sum() > 40
-    scale = np.maximum(1.0, np.abs(mean0[ok]).max(axis=1, keepdims=True))
-    assert np.all(np.abs(mean[ok] - mean0[ok]) <= 1e-7 * scale)
-    assert np.all(np.abs(chi2[ok] - chi20[ok]) <= 1e-9 * np.abs(chi20[ok]))
+    n_ok = 0
+    for i, row in enumerate(theta):
+        if not np.isfinite(full[i]):
+            continue
+        mu, c2 = pr.gp_predict(dict(zip(names, map(float, row))), times)
+        assert np.abs(mean[i] - mu).max() <= 1e-7 * max(1.0, np.abs(mu).max()), (N, i)
+        assert abs(chi2[i] - c2) <= 1e-9 * max(1.0, c2), (N, i)
+        n_ok += 1
+    assert n_ok > 40
 
 
 @pytest.mark.gpu

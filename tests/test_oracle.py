@@ -162,6 +162,67 @@ def test_gp_conditioning_restatement_self_consistent():
                            rtol=1e-9, atol=1e-9)
 
 
+def _gp_sklearn_cases():
+    from ravest_b200 import workloads
+    g = load_golden("gp_sklearn")
+    for c in g["cases"]:
+        spec, theta = workloads.make_c5(n_samples=c["n_samples"], n_planets=c["n_planets"], n_epochs=c["n_epochs"],
+                                        seed=c["seed"])
+        assert np.array_equal(theta, np.asarray(c["theta"])), "workload generator drifted from the fixture"
+        yield c, spec, theta
+
+
+def test_gp_restatement_against_sklearn():
+    """De-self-reference the GP rows (a17, a18, f-4): the numpy and C restatements of gp.py:145-156 / fit.py:8047-8060 /
+    fit.py:7536-7554 / fit.py:5427-5429 against scikit-learn's GaussianProcessRegressor on the same kernel
+    (tests/golden/make_gp_sklearn.py).  1e-8 relative, written here."""
+    RTOL = 1e-8
+    n_rows = 0
+    for c, spec, theta in _gp_sklearn_cases():
+        pr = oracle_py.Problem(spec)
+        names = pr.free_names + pr.free_hyper
+        assert names == c["names"]
+        times = np.asarray(c["times"])
+        full_c = oracle_c.OracleProblem(spec).logprob(theta)
+        for i, row in enumerate(theta):
+            comb = dict(zip(names, map(float, row)))
+            if c["ll"][i] is None:
+                assert c["logprob"][i] == -np.inf and full_c[i] == -np.inf
+                continue
+            allp = pr.fixed | {k: comb[k] for k in pr.free_names}
+            allh = pr.fixed_hyper | {k: comb[k] for k in pr.free_hyper}
+            ll = pr.gp_log_likelihood(allp, allh)
+            assert abs(ll - c["ll"][i]) <= RTOL * max(1.0, abs(c["ll"][i])), (c["name"], i, ll, c["ll"][i])
+            mu, chi2 = pr.gp_predict(comb, times)
+            ref_mu = np.asarray(c["mean"][i])
+            assert np.all(np.abs(mu - ref_mu) <= RTOL * np.maximum(1.0, np.abs(ref_mu).max())), (c["name"], i)
+            assert abs(chi2 - c["chi2"][i]) <= RTOL * max(1.0, c["chi2"][i])
+            assert abs(full_c[i] - c["logprob"][i]) <= RTOL * max(1.0, abs(c["logprob"][i])), (c["name"], i)
+            n_rows += 1
+    assert n_rows >= 80
+
+
+def test_gp_sklearn_fixture_reproduces_live():
+    """The committed fixture is what scikit-learn returns here and now (skipped if scikit-learn is absent)."""
+    pytest.importorskip("sklearn")
+    import importlib.util, os
+    from conftest import GOLDEN
+    sp = importlib.util.spec_from_file_location("make_gp_sklearn", os.path.join(GOLDEN, "make_gp_sklearn.py"))
+    mod = importlib.util.module_from_spec(sp)
+    sp.loader.exec_module(mod)
+    for c, spec, theta in _gp_sklearn_cases():
+        pr = oracle_py.Problem(spec)
+        names = pr.free_names + pr.free_hyper
+        done = 0
+        for i, row in enumerate(theta):
+            if c["ll"][i] is None or done >= 3:
+                continue
+            ll, mu, chi2 = mod.sklearn_gp(pr, dict(zip(names, map(float, row))), np.asarray(c["times"]))
+            assert abs(ll - c["ll"][i]) <= 1e-10 * max(1.0, abs(ll))
+            assert np.allclose(mu, c["mean"][i], rtol=1e-9, atol=1e-9) and abs(chi2 - c["chi2"][i]) <= 1e-9 * max(1.0, chi2)
+            done += 1
+
+
 def test_gp_restatement_self_consistent():
     """GP parity is unpinned (tinygp absent): the C and numpy restatements must at least agree with each
     other and with slogdet + solve."""
@@ -253,3 +314,21 @@ def test_live_reference_if_present():
     ref = np.array([lp.log_probability(dict(zip(free, map(float, r)))) for r in theta])
     assert np.array_equal(oracle_py.Problem(spec).log_probability_batch(theta), ref, equal_nan=True)
     assert_logp_close(oracle_c.OracleProblem(spec).logprob(theta), ref, "live")
+
+
+@pytest.mark.parametrize("config", ["c2", "c3", "c4"])
+def test_oracles_on_full_size_reference_subsamples(config):
+    """tests/golden/c3_c4_subsample.json (reference outputs on rows of the FULL-SIZE BASELINE configs): the numpy
+    restatement is bit-identical, the C restatement within tolerance."""
+    import hashlib
+    from ravest_b200 import workloads
+    fx = [c for c in load_golden("c3_c4_subsample") if c["config"] == config][0]
+    spec, theta = getattr(workloads, fx["maker"])(fx["n_samples"])
+    rows = np.ascontiguousarray(theta[np.asarray(fx["index"])])
+    assert hashlib.sha256(rows.tobytes()).hexdigest() == fx["rows_sha256"]
+    ref = np.asarray(fx["logprob"], dtype=np.float64)
+    sub = slice(0, 60)
+    assert np.array_equal(oracle_py.Problem(spec).log_probability_batch(rows[sub]), ref[sub], equal_nan=True)
+    assert_logp_close(oracle_c.OracleProblem(spec).logprob(rows), ref, config)
+    ll, _ = oracle_c.OracleProblem(spec).parts(rows)
+    assert_logp_close(ll, np.asarray(fx["loglike"], dtype=np.float64), config + " loglike")
