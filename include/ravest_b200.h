@@ -125,10 +125,10 @@ int rvlp_logprob_batch(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples
                        double* out_dev, void* stream);
 
 /* Optional, synchronous: times the compiled shapes of the log-probability kernel on (up to 2^18 of) the caller's
- * rows and keeps the fastest for this context (the alternative shape must win by 2 %); *chosen (may be NULL) gets its
- * index.  The choice changes the
- * speed only - every shape produces identical bits (tests/test_gpu_parity.py). */
-int rvlp_ctx_autotune(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples, int32_t* chosen);
+ * rows - on `stream`, i.e. ordered after whatever wrote theta_dev there - and keeps the fastest for this context
+ * (median of five launches each; the alternative shape must win by 2 %); *chosen (may be NULL) gets its index.
+ * The choice changes the speed only - every shape produces identical bits (tests/test_gpu_parity.py). */
+int rvlp_ctx_autotune(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples, void* stream, int32_t* chosen);
 
 /* Diagnostic: force shape `variant` (0 or 1) of the log-probability kernel for this context. */
 int rvlp_ctx_set_variant(rvlp_ctx* ctx, int32_t variant);
@@ -142,6 +142,15 @@ int rvlp_logprob_batch_host(rvlp_ctx* ctx, const double* theta_host, int64_t n_s
  * lp (LogPrior.__call__ on the converted params, fit.py:3672-3691); either pointer may be NULL. */
 int rvlp_logprob_parts_batch(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples,
                              double* loglike_dev, double* logprior_dev, void* stream);
+
+/* Replaces Fitter.calculate_log_likelihood / calculate_chi2 / calculate_aicc / calculate_bic (fit.py:1361-1384,
+ * 1457-1554), batched over rows of theta (context column order; the fixed parameters come from the descriptor, as
+ * build_params_dict does, fit.py:1386-1455).  loglike_dev [S] is required (the others derive from it, exactly as the
+ * reference works backwards from LogLikelihood: chi2 = -2 ll - sum ln(2 pi var)); chi2_dev / aicc_dev / bic_dev [S] may
+ * be NULL.  k_free = the reference's `self.ndim` (number of free parameters); < 0 uses the context's ndim.
+ * RVLP_EINVAL "division by zero" when n_epochs - k - 1 == 0 and aicc is requested (Python raises there). */
+int rvlp_info_criteria_batch(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples, int32_t k_free,
+                             double* loglike_dev, double* chi2_dev, double* aicc_dev, double* bic_dev, void* stream);
 
 /* Replaces Fitter.calculate_rv_{planet,trend,total}_from_samples (fit.py:2690-2824):
  * out_dev is [S, n_times] row-major; rows whose planet parameters are invalid are NaN
@@ -186,8 +195,9 @@ int rvlp_gp_logprob_batch(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samp
  * `gp.condition(y = vel - gamma - planets - trend, X_test = times)` -> conditional mean) and
  * GPFitter._compute_gp_chi2 (fit.py:5386-5429).  mean_dev is [S, n_times] row-major (may be NULL with
  * n_times == 0), chi2_dev [S] (may be NULL).  Rows whose planet parameters or hyperparameters are invalid are
- * NaN (the reference raises there).  Requires n_hyper == 4.  The context keeps a grow-only device scratch of
- * n_samples x n_epochs doubles (beta = C^-1 r per sample) between calls; growing it synchronises the stream once. */
+ * NaN (the reference raises there).  Requires n_hyper == 4.  A scratch of n_samples x n_epochs doubles (beta = C^-1 r
+ * per sample) is taken from the device's stream-ordered pool for the duration of the call (cudaMallocAsync on
+ * `stream`): concurrent calls on different streams of one context are independent. */
 int rvlp_gp_predict_batch(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples,
                           const double* times_dev, int64_t n_times, double* mean_dev,
                           double* chi2_dev, void* stream);

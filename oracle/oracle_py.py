@@ -391,6 +391,22 @@ class Problem:
             out[i] = acc
         return out
 
+    # ------------------------------------------------------------------ information criteria (Appendix B.10)
+    def information_criteria(self, row) -> tuple[float, float, float, float]:
+        """fit.py:1361-1384, 1457-1554: (log-likelihood, chi2, AICc, BIC) for one row of free values."""
+        params = self.build_params(row)
+        ll = self.log_likelihood(params)
+        var = np.zeros_like(self.velerr_sq)
+        for j, inst in enumerate(self.unique):                                   # fit.py:1493-1497
+            mask = self.inst_idx == j
+            var[mask] = self.velerr_sq[mask] + params[f"jit_{inst}"] ** 2
+        penalty = np.sum(np.log(2 * np.pi * var))                                # fit.py:1499
+        chi2 = -2 * ll - penalty                                                 # fit.py:1500
+        k, n = len(self.free_names), len(self.time)
+        aicc = (2 * k - 2 * ll) + (2 * k ** 2 + 2 * k) / (n - k - 1)             # fit.py:1526-1529
+        bic = k * np.log(n) - 2 * ll                                             # fit.py:1554
+        return float(ll), float(chi2), float(aicc), float(bic)
+
     # ------------------------------------------------------------------ walker checks (row f-3)
     def walker_stage(self, row) -> tuple[str, float | None]:
         """What fit.py:1048-1062 (and the retry loops fit.py:692-725, 884-902) decide for one candidate row:

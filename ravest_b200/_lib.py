@@ -30,6 +30,7 @@ EXPORTS = [
     "rvlp_kepler_rv", "rvlp_planet_rv", "rvlp_trend_rv", "rvlp_convert_to_default", "rvlp_prior_eval",
     "rvlp_measure_fp64_peak", "rvlp_launch_count", "rvlp_rv_batch_frozen", "rvlp_walker_check_batch",
     "rvlp_gp_predict_batch", "rvlp_percentile_workspace_bytes", "rvlp_percentile_columns", "rvlp_ctx_autotune", "rvlp_ctx_set_variant",
+    "rvlp_info_criteria_batch",
 ]
 MAX_FROZEN = 16
 MAX_PERCENTILES = 8
@@ -90,8 +91,9 @@ def load() -> C.CDLL:
     lib.rvlp_convert_to_default.argtypes = [i32, vp, i64, vp, vp, C.c_int, vp]
     lib.rvlp_prior_eval.argtypes = [C.POINTER(PriorPOD), vp, i64, vp, C.c_int, vp]
     lib.rvlp_measure_fp64_peak.argtypes = [C.c_int, C.c_int, C.POINTER(dbl), C.POINTER(dbl)]
-    lib.rvlp_ctx_autotune.argtypes = [vp, vp, i64, C.POINTER(i32)]
+    lib.rvlp_ctx_autotune.argtypes = [vp, vp, i64, vp, C.POINTER(i32)]
     lib.rvlp_ctx_set_variant.argtypes = [vp, i32]
+    lib.rvlp_info_criteria_batch.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, vp]
     lib.rvlp_rv_batch_frozen.argtypes = [vp, vp, i64, vp, i64, i32, i32, vp, vp, vp, vp]
     lib.rvlp_walker_check_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     lib.rvlp_gp_predict_batch.argtypes = [vp, vp, i64, vp, i64, vp, vp, vp]
@@ -241,7 +243,7 @@ class Context:
         """Pick the fastest compiled shape of the log-probability kernel for this problem (synchronous, once)."""
         th = self._theta(theta)
         chosen = C.c_int32(0)
-        check(self._lib.rvlp_ctx_autotune(self._h, th.data_ptr(), th.shape[0], C.byref(chosen)))
+        check(self._lib.rvlp_ctx_autotune(self._h, th.data_ptr(), th.shape[0], stream_ptr(self.device), C.byref(chosen)))
         self.k1_variant = int(chosen.value)
         return self.k1_variant
 
@@ -269,6 +271,19 @@ class Context:
         check(self._lib.rvlp_logprob_parts_batch(self._h, th.data_ptr(), th.shape[0], ll.data_ptr(),
                                                  lp.data_ptr(), stream_ptr(self.device)))
         return ll, lp
+
+    def info_criteria(self, theta, k_free: int = -1):
+        """(loglike, chi2, aicc, bic) tensors [S] - rvlp_info_criteria_batch (fit.py:1361-1554)."""
+        torch = _torch()
+        th = self._theta(theta)
+        out = [torch.empty(th.shape[0], dtype=torch.float64, device=th.device) for _ in range(4)]
+        rc = self._lib.rvlp_info_criteria_batch(self._h, th.data_ptr(), th.shape[0], int(k_free), out[0].data_ptr(),
+                                                out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),
+                                                stream_ptr(self.device))
+        if rc == -1 and b"division by zero" in self._lib.rvlp_last_error():
+            raise ZeroDivisionError("division by zero")            # (2k^2 + 2k) / (n - k - 1), fit.py:1528
+        check(rc)
+        return tuple(out)
 
     def logprob_host(self, theta_np: np.ndarray, out_np: np.ndarray | None = None) -> np.ndarray:
         """NumPy in, NumPy out through rvlp_logprob_batch_host (H2D + kernel + D2H inside)."""

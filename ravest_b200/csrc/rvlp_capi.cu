@@ -8,7 +8,9 @@
 #include <climits>
 #include <cstdlib>
 #include <cmath>
+#include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -81,6 +83,19 @@ int ensure_tables(int device) {
   return RVLP_OK;
 }
 
+// Per-device one-time setup of the default stream-ordered memory pool: keep freed blocks (no trim at synchronisation
+// points), so that per-call scratch (rvlp_gp_predict_batch) costs no driver allocation in steady state.
+int ensure_pool(int device) {
+  static std::atomic<uint64_t> done{0};
+  if (device < 64 && (done.load() >> device) & 1) return RVLP_OK;
+  cudaMemPool_t pool;
+  CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+  unsigned long long keep = ~0ull;
+  CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  if (device < 64) done.fetch_or(1ull << device);
+  return RVLP_OK;
+}
+
 int simple_grid(int64_t n) {
   int64_t g = (n + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
@@ -113,7 +128,11 @@ static K1Shape k1_shape(int v, const DevProblem& P, const SmemLayout& L) {
   return s;
 }
 
-constexpr int kTicketRing = 256;   // launches in flight per context before a counter is reused
+// Batch-ticket counters for the dynamic schedule of logprob_kernel / rv_matrix_kernel.  A launch takes the next slot of
+// the ring; the slot carries an event recorded right after the kernel that used it, and a later launch that lands on
+// the same slot first makes ITS stream wait for that event.  Any number of launches may therefore be in flight on any
+// number of streams: a counter is never reset or shared while a kernel still reads it.
+constexpr int kTicketRing = 256;
 
 struct rvlp_ctx {
   int device = 0;
@@ -123,8 +142,6 @@ struct rvlp_ctx {
   void* d_priors = nullptr;
   void* d_epochs = nullptr;
   int smem_main = 0, smem_gp = 0, smem_gp_tiled = 0, smem_gp_blocked = 0, smem_gp_pipe = 0, smem_gp_pipe_pred = 0, gp_tile = 0, smem_gp_predict = 0;
-  double* d_beta = nullptr;      // K7 scratch: beta = C^-1 r per sample, [beta_rows, n_epochs]
-  int64_t beta_rows = 0;
   int max_smem = 0;
   int k1 = 0;          // K1 variant in use
   int k1_tuned = 0;    // rvlp_ctx_autotune has run
@@ -135,7 +152,12 @@ struct rvlp_ctx {
   double* d_out = nullptr;
   int64_t cap_samples = 0;
   unsigned long long* d_tickets = nullptr;   // ring of batch-ticket counters for logprob_kernel's dynamic schedule
-  std::atomic<unsigned> ticket_slot{0};
+  cudaEvent_t ticket_ev[kTicketRing] = {};   // completion of the last kernel that used the slot
+  unsigned ticket_next = 0;
+  std::mutex ticket_mu;                      // slot hand-out + (wait, memset, launch, record) is one critical section
+  cudaEvent_t ev_done[8] = {};               // host-buffer path: one per chunk, created once
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr;   // autotune timing
+  std::mutex host_mu;                        // the host-buffer path owns the staging buffers: one call at a time
   cudaStream_t stream = nullptr;    // host-buffer path: chunks alternate between two streams so that
   cudaStream_t stream2 = nullptr;   // the H2D copy of chunk i+1 overlaps the kernel of chunk i
 };
@@ -279,6 +301,10 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_blocked_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   }
   CTX_TRY(cudaMalloc((void**)&c->d_tickets, sizeof(unsigned long long) * kTicketRing));
+  for (int i = 0; i < kTicketRing; ++i) CTX_TRY(cudaEventCreateWithFlags(&c->ticket_ev[i], cudaEventDisableTiming));
+  for (int i = 0; i < 8; ++i) CTX_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+  CTX_TRY(cudaEventCreate(&c->ev_a));
+  CTX_TRY(cudaEventCreate(&c->ev_b));
   CTX_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CTX_TRY(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
 #undef CTX_TRY
@@ -296,7 +322,12 @@ void rvlp_ctx_destroy(rvlp_ctx* c) {
   cudaFree(c->d_theta);
   cudaFree(c->d_out);
   cudaFree(c->d_tickets);
-  cudaFree(c->d_beta);
+  for (int i = 0; i < kTicketRing; ++i)
+    if (c->ticket_ev[i]) cudaEventDestroy(c->ticket_ev[i]);
+  for (int i = 0; i < 8; ++i)
+    if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+  if (c->ev_a) cudaEventDestroy(c->ev_a);
+  if (c->ev_b) cudaEventDestroy(c->ev_b);
   if (c->h_theta) cudaFreeHost(c->h_theta);
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -322,12 +353,19 @@ static int launch_logprob(rvlp_ctx* c, const double* theta, int64_t S, double* o
   if (per_warp / 4 > kG) nb = (int)(per_warp / 4 < shape.max_nb ? per_warp / 4 : shape.max_nb);
   const int64_t want = ((S + nb - 1) / nb + shape.workers - 1) / shape.workers;
   if (want < grid) grid = (int)want;
-  unsigned long long* tickets = nullptr;
   if (per_warp >= 2) {                                     // several batches per warp: dynamic schedule
-    tickets = c->d_tickets + (c->ticket_slot.fetch_add(1) % kTicketRing);
+    std::lock_guard<std::mutex> lock(c->ticket_mu);
+    const unsigned slot = c->ticket_next++ % kTicketRing;
+    unsigned long long* tickets = c->d_tickets + slot;
+    CUDA_TRY(cudaStreamWaitEvent(st, c->ticket_ev[slot], 0));   // the slot's previous user (any stream) has finished
     CUDA_TRY(cudaMemsetAsync(tickets, 0, sizeof(unsigned long long), st));
+    kern<<<grid, shape.threads, smem, st>>>(c->P, theta, S, out, ll, lp, nb, tickets);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ticket_ev[slot], st));
+    return RVLP_OK;
   }
-  kern<<<grid, shape.threads, smem, st>>>(c->P, theta, S, out, ll, lp, nb, tickets);
+  kern<<<grid, shape.threads, smem, st>>>(c->P, theta, S, out, ll, lp, nb, nullptr);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return RVLP_OK;
@@ -347,40 +385,48 @@ int rvlp_ctx_set_variant(rvlp_ctx* c, int32_t variant) {
   return RVLP_OK;
 }
 
-int rvlp_ctx_autotune(rvlp_ctx* c, const double* theta_dev, int64_t S, int32_t* chosen) {
+int rvlp_ctx_autotune(rvlp_ctx* c, const double* theta_dev, int64_t S, void* stream, int32_t* chosen) {
   if (!c || S < 0 || (S > 0 && !theta_dev)) return fail(RVLP_EINVAL, "bad arguments");
   if (chosen) *chosen = c->k1;
   if (c->P.n_hyper || S < 4096) return RVLP_OK;             // nothing to choose for GP contexts / tiny batches
   DeviceGuard guard(c->device);
+  // Timed on the CALLER's stream: the launches are ordered after whatever produced theta_dev there (timing rows that
+  // are still being written would measure garbage - e.g. all-invalid rows skip the likelihood - and latch the wrong
+  // shape for the context's lifetime).
+  cudaStream_t st = (cudaStream_t)stream;
   // the whole batch up to 2^18 rows: the prologue batch size and the number of batches per warp depend on the row count,
   // so a short prefix can favour the wrong shape (c2 at 1e5 rows flipped between runs with a 65 536-row prefix)
   const int64_t n = S < 262144 ? S : 262144;
   double* scratch = nullptr;
   CUDA_TRY(cudaMalloc((void**)&scratch, sizeof(double) * (size_t)n));
-  cudaEvent_t a, b;
-  CUDA_TRY(cudaEventCreate(&a));
-  CUDA_TRY(cudaEventCreate(&b));
-  float best = 1e30f;
-  int best_v = 0, rc = RVLP_OK;
+  const int prev = c->k1;
+  float med[kK1Variants];
+  int rc = RVLP_OK;
   for (int v = 0; v < kK1Variants && rc == RVLP_OK; ++v) {
     c->k1 = v;
-    float tmin = 1e30f;
-    for (int rep = 0; rep < 3 && rc == RVLP_OK; ++rep) {    // first repetition doubles as warm-up
-      cudaEventRecord(a, c->stream);
-      rc = launch_logprob(c, theta_dev, n, scratch, nullptr, nullptr, c->stream);
-      cudaEventRecord(b, c->stream);
-      if (cudaEventSynchronize(b) != cudaSuccess) rc = fail(RVLP_ECUDA, "autotune launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    float t[5];
+    for (int rep = -1; rep < 5 && rc == RVLP_OK; ++rep) {    // one warm-up, then the MEDIAN of five (a min-of-two once
+      cudaEventRecord(c->ev_a, st);                           // mis-picked under a profiler and cost 9 %)
+      rc = launch_logprob(c, theta_dev, n, scratch, nullptr, nullptr, st);
+      cudaEventRecord(c->ev_b, st);
+      if (rc == RVLP_OK && cudaEventSynchronize(c->ev_b) != cudaSuccess)
+        rc = fail(RVLP_ECUDA, "autotune launch failed: %s", cudaGetErrorString(cudaGetLastError()));
       float ms = 0;
-      cudaEventElapsedTime(&ms, a, b);
-      if (rep > 0 && ms < tmin) tmin = ms;
+      if (rc == RVLP_OK) cudaEventElapsedTime(&ms, c->ev_a, c->ev_b);
+      if (rep >= 0) t[rep] = ms;
     }
-    if (tmin < (v == 0 ? best : 0.98f * best)) { best = tmin; best_v = v; }   // the alternative shape must win by 2 %
+    if (rc == RVLP_OK) {
+      std::sort(t, t + 5);
+      med[v] = t[2];
+    }
   }
-  cudaEventDestroy(a);
-  cudaEventDestroy(b);
   cudaFree(scratch);
-  c->k1 = rc == RVLP_OK ? best_v : 0;
-  c->k1_tuned = 1;
+  int best_v = 0;
+  if (rc == RVLP_OK)
+    for (int v = 1; v < kK1Variants; ++v)
+      if (med[v] < 0.98f * med[best_v]) best_v = v;          // an alternative shape must win by 2 %
+  c->k1 = rc == RVLP_OK ? best_v : prev;
+  c->k1_tuned = rc == RVLP_OK;
   if (chosen) *chosen = c->k1;
   return rc;
 }
@@ -393,6 +439,27 @@ int rvlp_logprob_parts_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, do
   DeviceGuard guard(c->device);
   // ll_out non-null forces the likelihood to be evaluated even for rows the prior rejects
   return launch_logprob(c, theta_dev, S, nullptr, ll_dev, lp_dev, (cudaStream_t)stream);
+}
+
+int rvlp_info_criteria_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, int32_t k_free, double* ll_dev,
+                             double* chi2_dev, double* aicc_dev, double* bic_dev, void* stream) {
+  if (!c || S < 0 || (S > 0 && (!theta_dev || !ll_dev))) return fail(RVLP_EINVAL, "bad arguments (loglike_dev is required)");
+  if (c->P.n_hyper) return fail(RVLP_EINVAL, "GP context not supported here");
+  const int64_t k = k_free >= 0 ? k_free : c->P.ndim, n = c->P.n_epochs;
+  if (aicc_dev && n - k - 1 == 0) return fail(RVLP_EINVAL, "division by zero");     // Python's ZeroDivisionError, fit.py:1528
+  if (S == 0) return RVLP_OK;
+  DeviceGuard guard(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = launch_logprob(c, theta_dev, S, nullptr, ll_dev, nullptr, st)) return rc;
+  if (!chi2_dev && !aicc_dev && !bic_dev) return RVLP_OK;
+  const double corr = aicc_dev ? (double)(2 * k * k + 2 * k) / (double)(n - k - 1) : 0.0;
+  int64_t g = (S + 7) / 8;
+  if (g > 148 * 16) g = 148 * 16;
+  info_criteria_kernel<<<(int)g, 256, 0, st>>>(c->P, theta_dev, S, ll_dev, chi2_dev, aicc_dev, bic_dev, (double)(2 * k), corr,
+                                               (double)k * log((double)n));
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return RVLP_OK;
 }
 
 // Pageable -> pinned staging copy.  One thread moves ~8 GB/s, which made the NumPy-in path copy-bound (33 ms against a
@@ -424,6 +491,7 @@ int rvlp_logprob_batch_host(rvlp_ctx* c, const double* theta_host, int64_t S, do
   if (!c || S < 0 || (S > 0 && (!theta_host || !out_host))) return fail(RVLP_EINVAL, "bad arguments");
   if (S == 0) return RVLP_OK;
   DeviceGuard guard(c->device);
+  std::lock_guard<std::mutex> host_lock(c->host_mu);
   if (S > c->cap_samples) {
     cudaFree(c->d_theta); cudaFree(c->d_out);
     if (c->h_theta) cudaFreeHost(c->h_theta);
@@ -473,8 +541,7 @@ int rvlp_logprob_batch_host(rvlp_ctx* c, const double* theta_host, int64_t S, do
   } else {
     bounds[nchunks++] = S;
   }
-  cudaEvent_t done[8];
-  for (int i = 0; i < nchunks; ++i) CUDA_TRY(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+  cudaEvent_t* done = c->ev_done;          // created once with the context
   int64_t s0 = 0;
   int rc = RVLP_OK;
   for (int ci = 0; ci < nchunks && rc == RVLP_OK; s0 = bounds[ci], ++ci) {
@@ -506,7 +573,6 @@ int rvlp_logprob_batch_host(rvlp_ctx* c, const double* theta_host, int64_t S, do
   }
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->stream2);
-  for (int i = 0; i < nchunks; ++i) cudaEventDestroy(done[i]);
   return rc;
 }
 
@@ -538,13 +604,22 @@ int rvlp_rv_batch_frozen(rvlp_ctx* c, const double* theta_dev, int64_t S, const 
   const int64_t want = ((S + kG - 1) / kG + kWarps - 1) / kWarps;
   int rc = grid_for(c->device, (const void*)rv_matrix_kernel, c->smem_main, want, &grid);
   if (rc) return rc;
-  unsigned long long* tickets = nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
   if (want >= 2 * (int64_t)grid) {                           // several batches per warp: dynamic schedule
-    tickets = c->d_tickets + (c->ticket_slot.fetch_add(1) % kTicketRing);
-    CUDA_TRY(cudaMemsetAsync(tickets, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+    std::lock_guard<std::mutex> lock(c->ticket_mu);
+    const unsigned slot = c->ticket_next++ % kTicketRing;
+    unsigned long long* tickets = c->d_tickets + slot;
+    CUDA_TRY(cudaStreamWaitEvent(st, c->ticket_ev[slot], 0));
+    CUDA_TRY(cudaMemsetAsync(tickets, 0, sizeof(unsigned long long), st));
+    rv_matrix_kernel<<<grid, kThreads, c->smem_main, st>>>(c->P, theta_dev, S, times_dev, T, component, out_dev, frozen,
+                                                          tickets);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->ticket_ev[slot], st));
+    return RVLP_OK;
   }
-  rv_matrix_kernel<<<grid, kThreads, c->smem_main, (cudaStream_t)stream>>>(c->P, theta_dev, S, times_dev, T,
-                                                                           component, out_dev, frozen, tickets);
+  rv_matrix_kernel<<<grid, kThreads, c->smem_main, st>>>(c->P, theta_dev, S, times_dev, T, component, out_dev, frozen,
+                                                        nullptr);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return RVLP_OK;
@@ -656,13 +731,16 @@ int rvlp_gp_predict_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const
     DeviceGuard guard(c->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int N = c->P.n_epochs;
-    if (c->beta_rows < S) {                       // grow-only scratch; reallocation synchronises, steady state does not
-      CUDA_TRY(cudaStreamSynchronize(st));
-      cudaFree(c->d_beta);
-      c->d_beta = nullptr; c->beta_rows = 0;
-      CUDA_TRY(cudaMalloc((void**)&c->d_beta, sizeof(double) * (size_t)S * N));
-      c->beta_rows = S;
-    }
+    // beta = C^-1 r scratch [S, N]: allocated per call from the device's stream-ordered pool (no host sync in steady
+    // state once the pool has grown; concurrent calls on different streams never share it) and released on `st` after
+    // the mean kernel.
+    if (int prc = ensure_pool(c->device)) return prc;
+    double* d_beta = nullptr;
+    CUDA_TRY(cudaMallocAsync((void**)&d_beta, sizeof(double) * (size_t)S * N, st));
+    struct BetaFree {
+      double* p; cudaStream_t st;
+      ~BetaFree() { cudaFreeAsync(p, st); }
+    } beta_free{d_beta, st};
     int grid = 0, rc = RVLP_OK;
     const char* grid_cap = getenv("RVLP_GP_GRID");        // tests / experiments: cap the grid
 #define RVLP_GP_PRED(TT)                                                                                          \
@@ -670,7 +748,7 @@ int rvlp_gp_predict_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const
     rc = grid_for(c->device, (const void*)gp_logprob_pipe_kernel<TT, true>, c->smem_gp_pipe_pred, S, &grid);      \
     if (rc) return rc;                                                                                            \
     if (grid_cap && atoi(grid_cap) > 0 && atoi(grid_cap) < grid) grid = atoi(grid_cap);                           \
-    gp_logprob_pipe_kernel<TT, true><<<grid, kThreads, c->smem_gp_pipe_pred, st>>>(c->P, theta_dev, S, chi2_dev, c->d_beta); \
+    gp_logprob_pipe_kernel<TT, true><<<grid, kThreads, c->smem_gp_pipe_pred, st>>>(c->P, theta_dev, S, chi2_dev, d_beta); \
     break;
     switch (c->gp_tile) {
       RVLP_GP_PRED(2) RVLP_GP_PRED(4) RVLP_GP_PRED(6) RVLP_GP_PRED(8) RVLP_GP_PRED(10)
@@ -683,7 +761,7 @@ int rvlp_gp_predict_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const
       const int smem_mean = 4 * ((N + 1) & ~1) * 8;
       rc = grid_for(c->device, (const void*)gp_mean_kernel, smem_mean, S, &grid);
       if (rc) return rc;
-      gp_mean_kernel<<<grid, kThreads, smem_mean, st>>>(c->P, theta_dev, S, c->d_beta, times_dev, T, mean_dev);
+      gp_mean_kernel<<<grid, kThreads, smem_mean, st>>>(c->P, theta_dev, S, d_beta, times_dev, T, mean_dev);
       ++g_launches;
       CUDA_TRY(cudaGetLastError());
     }
@@ -752,13 +830,14 @@ int rvlp_percentile_columns(const double* A_dev, int64_t S, int64_t T, const dou
   CUDA_TRY(cudaMemsetAsync(W.hist, 0, (size_t)T * R * 256 * 4, st));   // level 0 accumulates into buffer 0
   CUDA_TRY(cudaMemsetAsync(W.mode, 0xff, (size_t)T * 4, st));          // -1: every column streams
   CUDA_TRY(cudaMemsetAsync(W.ncand, 0, (size_t)2 * T * 4, st));        // candidate counters + NaN flags
-  static bool attr_done = false;
-  if (!attr_done) {
+  // cudaFuncSetAttribute is per DEVICE: one bit per device, as ensure_tables does
+  static std::atomic<uint64_t> attr_done{0};
+  if (device >= 64 || !((attr_done.load() >> device) & 1)) {
     CUDA_TRY(cudaFuncSetAttribute(band_level_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(1, kMaxTargets)));
     CUDA_TRY(cudaFuncSetAttribute(band_level_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(1, kMaxTargets)));
     CUDA_TRY(cudaFuncSetAttribute(band_level_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(1, kMaxTargets)));
     CUDA_TRY(cudaFuncSetAttribute(band_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinishSmem));
-    attr_done = true;
+    if (device < 64) attr_done.fetch_or(1ull << device);
   }
   int sms = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));

@@ -388,6 +388,15 @@ __device__ __forceinline__ void chi_epilogue(const DevProblem& P, const Tables& 
   }
 }
 
+// prodm is a running product of mantissas in [1, 2): it overflows after ~1023 factors per lane (n_epochs >= 32 768,
+// i.e. only the epochs-in-global-memory shape).  Folding its exponent into exsum every <= 512 factors keeps it a
+// normal number for any epoch count; scaling by a power of two is exact, so ln(prod var) is unchanged.
+__device__ __forceinline__ void chi_renorm(ChiAcc& a) {
+  const int h = __double2hiint(a.prodm);
+  a.exsum += (h >> 20) - 1023;
+  a.prodm = __hiloint2double((h & 0x000fffff) | 0x3ff00000, __double2loint(a.prodm));
+}
+
 __device__ __forceinline__ double chi_finish(const ChiAcc& a) {
   // prodm is a product of mantissas in [1, 2): positive and normal unless it overflowed (> 1023 epochs per lane)
   const double lm = __double2hiint(a.prodm) < 0x7ff00000 ? log_pos_normal(a.prodm) : log(a.prodm);
@@ -557,6 +566,7 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
             for (int j = 0; j < W; ++j) tt[j] = T.t[base + j * 32 + lane];
             model_rv<W>(P, sr, tt, rv, -1, true);
             chi_epilogue<W>(P, T, sr, base, lane, rv, acc);
+            if (GE && ((base / (32 * W)) & 127) == 127) chi_renorm(acc);   // <= 128 W = 512 factors between folds
           }
         }
         ll = -0.5 * chi_finish(acc);
@@ -683,6 +693,42 @@ walker_check_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, i
       if (lhp_out) lhp_out[s] = lhp;
     }
     __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ information criteria (fit.py:1361-1554)
+// Fitter.calculate_chi2 works backwards from the log-likelihood: penalty = sum_i ln(2 pi (sigma_i^2 + jit_inst(i)^2)),
+// chi2 = -2 ll - penalty (fit.py:1485-1500); AICc = 2k - 2 ll + (2k^2 + 2k) / (n - k - 1) (fit.py:1524-1529);
+// BIC = k ln n - 2 ll (fit.py:1553-1554).  One warp per row: the penalty depends on the row's jitter values only;
+// lanes walk the epochs in a fixed order and fold with one butterfly (bits independent of the grid).
+__global__ void __launch_bounds__(256)
+info_criteria_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, const double* __restrict__ ll,
+                     double* __restrict__ chi2, double* __restrict__ aicc, double* __restrict__ bic, double two_k,
+                     double aicc_corr, double k_ln_n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const double* e2 = P.epochs + 2 * (size_t)P.n_pad;
+  const int* inst = reinterpret_cast<const int*>(P.epochs + 3 * (size_t)P.n_pad);
+  const int i_jit = 5 * P.n_planets + 2 + P.n_inst;
+  for (int64_t s = gw; s < S; s += nw) {
+    const double* row = theta + s * P.ndim;
+    double pen = 0.0;
+    if (chi2) {
+      for (int i = lane; i < P.n_epochs; i += 32) {
+        const int q = i_jit + inst[i];
+        const int c = P.src_col[q];
+        const double jit = c >= 0 ? row[c] : P.src_const[q];
+        pen += log((2 * PI_D) * (e2[i] + jit * jit));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) pen += __shfl_xor_sync(0xffffffffu, pen, o);
+    }
+    if (lane == 0) {
+      const double l = ll[s];
+      if (chi2) chi2[s] = -2 * l - pen;
+      if (aicc) aicc[s] = (two_k - 2 * l) + aicc_corr;
+      if (bic) bic[s] = k_ln_n - 2 * l;
+    }
   }
 }
 

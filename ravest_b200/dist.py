@@ -52,6 +52,10 @@ def sharded_logprob(eval_fn: Callable, theta, n_samples: int | None = None, grou
         raise ValueError(f"rank {rank}: local block has {local.shape[0]} rows, expected {hi - lo}")
     part = eval_fn(local) if hi > lo else torch.empty(0, dtype=torch.float64, device=theta.device)
     m = max_shard(S, world)
+    if m * world == S:                   # equal shards (the usual case): gather straight into the result
+        out = torch.empty(S, dtype=torch.float64, device=part.device)
+        dist.all_gather_into_tensor(out, part.contiguous(), group=group)
+        return out
     send = torch.full((m,), float("nan"), dtype=torch.float64, device=part.device)
     send[: hi - lo] = part
     recv = torch.empty(world * m, dtype=torch.float64, device=part.device)

@@ -282,6 +282,33 @@ class LogPosterior(_DeviceBacked, _SampleMatrices):
         """(log-likelihood, log-prior) per row, for diagnostics / information criteria."""
         return self.ctx.logprob_parts(_lib.as_cuda_f64(theta))
 
+    # -- information criteria (Fitter.calculate_log_likelihood / chi2 / aicc / bic, fit.py:1361-1554) ----------
+    def information_criteria_batch(self, theta) -> dict:
+        """{"loglike", "chi2", "aicc", "bic"}: CUDA tensors [S] for rows of free-parameter values (fixed parameters are
+        merged in as `Fitter.build_params_dict` does, fit.py:1386-1455); k = number of free parameters (`Fitter.ndim`)."""
+        ll, chi2, aicc, bic = self.ctx.info_criteria(theta, k_free=len(self.free_params_names))
+        return {"loglike": ll, "chi2": chi2, "aicc": aicc, "bic": bic}
+
+    def _criteria_of(self, params_dict: Dict[str, float]) -> dict:
+        row = np.array([[float(params_dict[n]) for n in self.free_params_names]])
+        return {k: float(v[0]) for k, v in self.information_criteria_batch(row).items()}
+
+    def calculate_log_likelihood(self, params_dict: Dict[str, float]) -> float:
+        """fit.py:1361-1384 (params_dict holds ALL parameters; the fixed ones must equal this object's)."""
+        return self._criteria_of(params_dict)["loglike"]
+
+    def calculate_chi2(self, params_dict: Dict[str, float]) -> float:
+        """fit.py:1457-1502."""
+        return self._criteria_of(params_dict)["chi2"]
+
+    def calculate_aicc(self, params_dict: Dict[str, float]) -> float:
+        """fit.py:1504-1530."""
+        return self._criteria_of(params_dict)["aicc"]
+
+    def calculate_bic(self, params_dict: Dict[str, float]) -> float:
+        """fit.py:1532-1554."""
+        return self._criteria_of(params_dict)["bic"]
+
     # -- the reference's scalar conventions ------------------------------------------
     def log_probability(self, free_params_dict: Dict[str, float]) -> float:
         """fit.py:3448-3495."""

@@ -4,7 +4,7 @@ Run in the build container only (needs /root/reference):
 
     python tests/golden/make_golden.py
 
-Writes tests/golden/{rv,tctp,priors,known_answers,logprob_cases,rv_matrix,sample_matrices,c3_c4_subsample}.json.
+Writes tests/golden/{rv,tctp,priors,known_answers,logprob_cases,rv_matrix,sample_matrices,c3_c4_subsample,info_criteria}.json.
 Every number in those files is an output of the reference's own code
 (`ravest.model.Planet.radial_velocity`, `Parameterisation.convert_*`, `ravest.prior.*`,
 `ravest.fit.LogPosterior.log_probability`, `Fitter.find_map_estimate`,
@@ -526,6 +526,26 @@ def make_full_size_subsamples():
     dump("c3_c4_subsample.json", out)
 
 
+def make_info_criteria():
+    """Appendix B.10: Fitter.calculate_log_likelihood / calculate_chi2 / calculate_aicc / calculate_bic
+    (fit.py:1361-1554) on rows of free-parameter values via the reference's own build_params_dict."""
+    out = []
+    for par, seed, inst in (("P K secosw sesinw Tc", 61, ("HARPS", "HIRES")), ("P K e w Tp", 62, ("A",)),
+                            ("P K e w Tc", 63, ("A", "B", "C"))):
+        spec, theta = workloads.make_multiplanet(2, 45, 40, seed, parameterisation=par, instruments=inst,
+                                                 t_span=200.0, invalid_frac=0.1)
+        f = ref_fitter(spec)
+        names = f.free_params_names
+        rows = []
+        for r in theta:
+            p = f.build_params_dict([float(x) for x in r])
+            rows.append([float(f.calculate_log_likelihood(p)), float(f.calculate_chi2(p)), float(f.calculate_aicc(p)),
+                         float(f.calculate_bic(p))])
+        out.append({"spec": spec, "free_names": names, "theta": theta, "ndim": int(f.ndim), "n_epochs": len(f.time),
+                    "loglike_chi2_aicc_bic": np.array(rows)})
+    dump("info_criteria.json", out)
+
+
 if __name__ == "__main__":
     import logging
     logging.disable(logging.CRITICAL)
@@ -537,3 +557,4 @@ if __name__ == "__main__":
     make_rv_matrix()
     make_sample_matrices()
     make_full_size_subsamples()
+    make_info_criteria()

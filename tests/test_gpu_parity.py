@@ -736,3 +736,109 @@ def test_gp_pipelined_kernels_are_run_to_run_deterministic(cuda, monkeypatch):
             if ref_lp is None:
                 ref_lp, ref_mean, ref_chi = lp, mean, chi2
             assert np.array_equal(lp, ref_lp) and np.array_equal(mean, ref_mean) and np.array_equal(chi2, ref_chi), rep
+
+
+# ------------------------------------------------------------------ round 2: information criteria, robustness
+def test_information_criteria_against_reference(cuda):
+    """Appendix B.10: batched calculate_log_likelihood / chi2 / aicc / bic (fit.py:1361-1554) against the values the
+    reference's Fitter returned for the same rows (tests/golden/info_criteria.json)."""
+    for c in load_golden("info_criteria"):
+        spec = spec_from_json(c["spec"])
+        post = _post(spec)
+        theta = np.asarray(c["theta"], dtype=np.float64)
+        res = post.information_criteria_batch(theta)
+        ref = np.asarray(c["loglike_chi2_aicc_bic"], dtype=np.float64)
+        for j, key in enumerate(("loglike", "chi2", "aicc", "bic")):
+            got = res[key].cpu().numpy()
+            # chi2 / aicc / bic are +inf where the log-likelihood is -inf (invalid planet)
+            assert np.array_equal(np.isinf(got), np.isinf(ref[:, j])) and np.array_equal(np.sign(got[np.isinf(got)]), np.sign(ref[np.isinf(got), j]))
+            fin = np.isfinite(ref[:, j])
+            tol = (2.0 if j else 1.0) * (1e-7 + 2e-13 * np.abs(ref[fin, 0]))      # derived from -2 ll
+            assert np.all(np.abs(got[fin] - ref[fin, j]) <= tol), (key, np.abs(got[fin] - ref[fin, j]).max())
+        names = c["free_names"]
+        full = {k: v[0] for k, v in spec["params"].items()} | dict(zip(names, map(float, theta[0])))
+        assert post.calculate_chi2(full) == res["chi2"][0].item() and post.calculate_bic(full) == res["bic"][0].item()
+        assert post.calculate_aicc(full) == res["aicc"][0].item()
+        assert post.calculate_log_likelihood(full) == res["loglike"][0].item()
+
+
+def test_more_than_a_ticket_ring_of_launches_in_flight_on_three_streams(cuda):
+    """The dynamic-schedule ticket counters (256-slot ring) are guarded by events: 900 launches queued round-robin on
+    three streams - far more than the ring - must all produce the single-launch bits (a reused live counter would skip
+    or duplicate batches)."""
+    from ravest_b200 import workloads
+    spec, theta = workloads.make_c2(60_000)
+    post = _post(spec)
+    th = cuda.as_tensor(theta, device="cuda")
+    base = post.ctx.logprob(th).cpu().numpy().view(np.int64)
+    streams = [cuda.cuda.Stream() for _ in range(3)]
+    outs = [cuda.empty(len(theta), dtype=cuda.float64, device="cuda") for _ in range(6)]
+    cuda.cuda.synchronize()
+    for i in range(900):
+        with cuda.cuda.stream(streams[i % 3]):
+            post.ctx.logprob(th, out=outs[i % 6])
+        if i % 6 == 5 and i >= 890:
+            pass
+    cuda.cuda.synchronize()
+    for o in outs:
+        assert np.array_equal(o.cpu().numpy().view(np.int64), base)
+    # interleaved with RV-matrix launches (they draw from the same ring)
+    times = cuda.linspace(0.0, 100.0, 64, dtype=cuda.float64, device="cuda")
+    m0 = post.ctx.rv_matrix(th, times, -2).cpu().numpy().view(np.int64)
+    ms = [cuda.empty((len(theta), 64), dtype=cuda.float64, device="cuda") for _ in range(3)]
+    for i in range(300):
+        with cuda.cuda.stream(streams[i % 3]):
+            post.ctx.rv_matrix(th, times, -2, out=ms[i % 3])
+            post.ctx.logprob(th, out=outs[i % 3])
+    cuda.cuda.synchronize()
+    for mm in ms:
+        assert np.array_equal(mm.cpu().numpy().view(np.int64), m0)
+    for o in outs[:3]:
+        assert np.array_equal(o.cpu().numpy().view(np.int64), base)
+
+
+def test_variance_mantissa_product_does_not_overflow_with_very_many_epochs(cuda):
+    """ChiAcc keeps sum ln var as a product of mantissas: 131 072 epochs = 4096 factors per lane with mantissa ~1.9
+    (1.9^4096 overflows a double) - the exponent is folded back every <= 512 factors."""
+    from oracle import oracle_c
+    from ravest_b200 import workloads
+    N = 131072
+    spec, theta = workloads.make_multiplanet(1, N, 24, seed=5, instruments=("A",), t_span=3000.0, invalid_frac=0.0,
+                                             fixed=("gd", "gdd"))
+    names = workloads.free_names(spec)
+    spec["velerr"] = np.full(N, np.sqrt(1.9 * 0.25))           # sigma^2 = 0.475 = 1.9 * 2^-2
+    theta[:, names.index("jit_A")] = 0.0                        # var = sigma^2 exactly
+    theta[1, names.index("jit_A")] = 1e-3
+    post = _post(spec)
+    got = post.log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
+    ref = oracle_c.OracleProblem(spec).logprob(theta, nthreads=8)
+    assert np.isfinite(ref).all() and np.isfinite(got).all()
+    assert_logp_close(got, ref, "N = 131072")
+
+
+def test_two_devices_in_one_process(cuda):
+    """Per-device state (function attributes, constant tables, memory pools): the same problem evaluated on cuda:0 and
+    cuda:1 from ONE process, including the percentile bands whose opt-in shared memory is a per-device attribute."""
+    if cuda.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    from ravest_b200 import _lib, fit, workloads
+    spec, theta = workloads.make_c2(20_000)
+    spec5, theta5 = workloads.make_c5(n_samples=64, n_planets=1, n_epochs=60, seed=4)
+    res = []
+    for dev in (0, 1):
+        post = fit.from_spec(spec)
+        post.device = dev
+        th = cuda.as_tensor(theta, device=f"cuda:{dev}")
+        with cuda.cuda.device(dev):
+            lp = post.log_probability_batch(th)
+            times = cuda.linspace(0.0, 100.0, 200, dtype=cuda.float64, device=f"cuda:{dev}")
+            m = post.ctx.rv_matrix(th, times, -2)
+            bands = _lib.percentile_columns(m, [15.85, 50, 84.15])
+            p5 = fit.from_spec(spec5)
+            p5.device = dev
+            g = p5.log_probability_batch(cuda.as_tensor(theta5, device=f"cuda:{dev}"))
+            mu = p5.ctx.gp_predict(cuda.as_tensor(theta5, device=f"cuda:{dev}"), np.linspace(0, 100, 11))
+        assert lp.device.index == dev and bands.device.index == dev
+        res.append([x.cpu().numpy() for x in (lp, bands, g, mu)])
+    for a, b in zip(*res):
+        assert np.array_equal(a.view(np.int64), b.view(np.int64))

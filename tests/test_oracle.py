@@ -332,3 +332,15 @@ def test_oracles_on_full_size_reference_subsamples(config):
     assert_logp_close(oracle_c.OracleProblem(spec).logprob(rows), ref, config)
     ll, _ = oracle_c.OracleProblem(spec).parts(rows)
     assert_logp_close(ll, np.asarray(fx["loglike"], dtype=np.float64), config + " loglike")
+
+
+def test_py_oracle_information_criteria_bit_exact():
+    """tests/golden/info_criteria.json: Fitter.calculate_log_likelihood / chi2 / aicc / bic of the reference."""
+    for c in load_golden("info_criteria"):
+        spec = spec_from_json(c["spec"])
+        pr = oracle_py.Problem(spec)
+        assert len(pr.free_names) == c["ndim"] and len(pr.time) == c["n_epochs"]
+        got = np.array([pr.information_criteria(r) for r in np.asarray(c["theta"])])
+        ref = np.asarray(c["loglike_chi2_aicc_bic"], dtype=np.float64)
+        assert np.array_equal(got, ref, equal_nan=True)
+        assert np.isneginf(ref[:, 0]).any() and np.isposinf(ref[:, 1]).any()
