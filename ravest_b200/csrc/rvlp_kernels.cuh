@@ -371,7 +371,11 @@ __device__ __forceinline__ void chi_epilogue(const DevProblem& P, const Tables& 
     const bool live = idx < P.n_epochs;
     odd |= live && !normal;
     if (live && normal) {                                 // fit.py:3655-3658
+#if RVLP_OPT & 2
+      a.chi = fma(res[j] * res[j], rcp64_3(var[j]), a.chi);
+#else
       a.chi = fma(res[j] * res[j], rcp64(var[j]), a.chi);
+#endif
       a.prodm *= __hiloint2double((h & 0x000fffff) | 0x3ff00000, __double2loint(var[j]));
       a.exsum += (h >> 20) - 1023;
       a.cnt += 1;
@@ -559,6 +563,30 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
           sample_chi_pipelined<kWP, 1, 0>(P, T, sr, lane, 4.0e-6, acc);
         } else if ((RVLP_PIPELINE & 2) && (flags & F_CLS_FULL)) {
           sample_chi_pipelined<kWP, 2, 1>(P, T, sr, lane, 2.5e-4, acc);
+        } else if ((RVLP_OPT & 32) && (flags & F_CLS_LITE)) {
+          // every planet takes the lite plan: no circular-orbit test, no plan dispatch, three LDS.128 per planet
+          const double2* planets = reinterpret_cast<const double2*>(sr + kHdr + 2 * P.n_inst);
+          const double c0 = sr[5], gd = sr[2], gdd = sr[3];
+          for (int base = 0; base < P.n_pad; base += 32 * W) {
+            double tt[W], rv[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+              tt[j] = T.t[base + j * 32 + lane];
+              rv[j] = c0;
+            }
+            for (int k = 0; k < P.n_planets; ++k) {
+              const double2* pr = planets + k * (kPlanetRec / 2);
+              const double2 a = pr[0], b = pr[1], c = pr[2];
+              planet_rv_add_lite<W>(a.x, a.y, b.x, b.y, c.x, c.y, tt, rv);
+            }
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+              const double dt = tt[j] - P.t0;                  // model.py:483-509
+              rv[j] = fma(gdd, dt * dt, fma(gd, dt, rv[j]));
+            }
+            chi_epilogue<W>(P, T, sr, base, lane, rv, acc);
+            if (GE && ((base / (32 * W)) & 127) == 127) chi_renorm(acc);
+          }
         } else {
           for (int base = 0; base < P.n_pad; base += 32 * W) {
             double tt[W], rv[W];

@@ -23,6 +23,17 @@
 #define RV_SLOW inline
 #endif
 
+// Micro-optimisation switches of the Kepler stage (bit mask; tools/kernel_sweep.py times them one by one):
+//   1  two-term Cody-Waite reduction (the third term is 1.3e-21 |M|, five orders below the rounding of M itself)
+//   2  reciprocals with fewer fp64 operations (one Newton step where 2^-40 suffices, e + e^2 correction elsewhere)
+//   4  fp32 <-> fp64 conversions of non-negative values by integer bit operations (ALU pipe) instead of F2F (XU
+//      pipe, 8 cycles per warp);  8  the signed one as well (five ALU instructions: costs more issue slots than it frees)
+//  16  one rejection test per group of W anomalies (integer max of the last steps / of |M|) instead of one per anomaly
+//  32  samples whose planets all take the lite plan (0 < e <= 0.65) run a loop without the per-planet plan dispatch
+#ifndef RVLP_OPT
+#define RVLP_OPT 51
+#endif
+
 namespace rvlp {
 
 // 2*pi split into 33 + 33 + 53 bits: k * TWO_PI_1 and k * TWO_PI_2 are exact for |k| < 2^20.
@@ -210,6 +221,85 @@ RV_HD double rcp64(double x) {
 #endif
 }
 
+// 1/x to ~2^-40 (one Newton step): enough where the result only scales a quantity that is itself ~1e-6 (the Newton
+// step of the lite plan) and the final reciprocal is re-derived against the true denominator afterwards.
+#if !defined(__CUDA_ARCH__)
+// host stand-in for MUFU.RCP64H (seed good to ~2^-20): worst-case relative error with a pseudo-random sign under
+// RVLP_EMULATE_MUFU, exact otherwise; the Newton steps below are the device's.
+inline double rcp64_seed_host(double x) {
+  double y = 1.0 / x;
+#if defined(RVLP_EMULATE_MUFU)
+  uint64_t b;
+  memcpy(&b, &x, 8);
+  b *= 0x9E3779B97F4A7C15ull;
+  y *= (b >> 63) ? (1.0 + 9.6e-7) : (1.0 - 9.6e-7);
+#endif
+  return y;
+}
+#endif
+RV_HD double rcp64_40(double x) {
+  double y;
+#if defined(__CUDA_ARCH__)
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+  y = rcp64_seed_host(x);
+#endif
+  const double e = ffma(-x, y, 1.0);
+  return ffma(y, e, y);
+}
+
+// 1/x to round-off in three fp64 operations: seed (2^-20), e = 1 - x y, y (1 + e + e^2); e^3 ~ 1e-18.
+RV_HD double rcp64_3(double x) {
+  double y;
+#if defined(__CUDA_ARCH__)
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#else
+  y = rcp64_seed_host(x);
+#endif
+  const double e = ffma(-x, y, 1.0);
+  return ffma(y, ffma(e, e, e), y);
+}
+
+// fp32 <-> fp64 by integer bit operations.  f2d_pos: x >= 0 (x = 0 gives 2^-127, denormals are off by < 2^-126: both
+// are absolute errors of < 1.2e-38 on an angle).  f2d_signed: any finite x.  d2f_trunc: 0 <= x < 2^127, truncating
+// (result <= x, within one fp32 ulp); anything below 2^-126 becomes 0.
+RV_HD double f2d_pos(float x) {
+#if defined(__CUDA_ARCH__) && (RVLP_OPT & 4)
+  const int b = __float_as_int(x);
+  return __hiloint2double((int)((unsigned)b >> 3) + 0x38000000, b << 29);
+#else
+  return (double)x;
+#endif
+}
+RV_HD double f2d_signed(float x) {
+#if defined(__CUDA_ARCH__) && (RVLP_OPT & 8)
+  const int b = __float_as_int(x);
+  const int mag = b & 0x7fffffff;
+  return __hiloint2double(((mag >> 3) + 0x38000000) | (b & (int)0x80000000), b << 29);
+#else
+  return (double)x;
+#endif
+}
+RV_HD float d2f_trunc(double x) {
+#if defined(__CUDA_ARCH__) && (RVLP_OPT & 4)
+  const int hi = __double2hiint(x);
+  const int f = __funnelshift_l(__double2loint(x), hi - 0x38000000, 3);
+  return __int_as_float(hi < 0x38100000 ? 0 : f);
+#elif (RVLP_OPT & 4)
+  // host build: same truncation, so that tests/host/solver_check.cpp sweeps what the device computes
+  float f = (float)x;
+  if ((double)f > x) {
+    uint32_t b;
+    memcpy(&b, &f, 4);
+    b -= 1;
+    memcpy(&f, &b, 4);
+  }
+  return x < 1.1754943508222875e-38 ? 0.0f : f;
+#else
+  return (float)x;
+#endif
+}
+
 RV_HD float rcp32(float x) {
 #if defined(__CUDA_ARCH__)
   float y;
@@ -293,7 +383,7 @@ RV_HD void sincos_0pi_table(float E0f, double& s, double& c) {
   const float t = ffmaf(E0f, 512.0f, 12582912.0f);       // 1.5 * 2^23 + rint(512 E0)
   const float jf = t - 12582912.0f;
   const float ebf = ffmaf(jf, -0.001953125f, E0f);        // E0 - j / 512, exact
-  const double eb = (double)ebf;
+  const double eb = f2d_signed(ebf);
 #if defined(__CUDA_ARCH__)
   // t = 1.5 * 2^23 + j: j sits in the low mantissa bits.  Masking (instead of subtracting the bias) gives an unsigned
   // 11-bit index: one LOP3 + one IMAD.WIDE.U32 for the address instead of five 64-bit integer instructions.
@@ -324,13 +414,15 @@ RV_HD bool anomaly_is_big(double M) {       // |M| >= BIG_M, inf or NaN, by an i
 }
 RV_HD void split_sign(double r, double& m, int& sign) {
   sign = hi32(r) & (int)0x80000000;
-  m = xor_hi(r, sign);
+  m = fabs(r);               // an operand modifier of the consuming fp64 instruction, not an instruction
 }
 RV_HD void reduce_anomaly(double M, double& m, int& sign) {
   const double k = ffma(M, RVK(14), RVK(15)) - RVK(15);
   double r = ffma(k, RVK(16), M);
   r = ffma(k, RVK(17), r);
+#if !(RVLP_OPT & 1)
   r = ffma(k, RVK(18), r);
+#endif
   split_sign(r, m, sign);
 }
 
@@ -398,7 +490,7 @@ RV_HD void kepler_stage_a(const double (&M)[W], double e, int n32, StarterOut<W>
 #pragma unroll
   for (int i = 0; i < W; ++i) {
     reduce_anomaly(M[i], o.m[i], o.sign[i]);
-    mf[i] = (float)o.m[i];
+    mf[i] = d2f_trunc(o.m[i]);
     float s, c;
     sincos_0pi_f32(mf[i], s, c);
     // q = |1 - e exp(i m)|^2 >= (1 - e)^2 > 0; a rounding-negative q gives NaN, which the clamp at the
@@ -440,7 +532,7 @@ RV_HD void kepler_stage_b(const StarterOut<W>& o, double e, int n64, double (&co
   double E[W], s[W], c[W];
 #pragma unroll
   for (int i = 0; i < W; ++i) {
-    E[i] = (double)o.Ef[i];
+    E[i] = f2d_pos(o.Ef[i]);
 #if RVLP_SINCOS_TABLE
     sincos_0pi_table(o.Ef[i], s[i], c[i]);
 #else
@@ -454,11 +546,21 @@ RV_HD void kepler_stage_b(const StarterOut<W>& o, double e, int n64, double (&co
       const double es = e * s[i];
       const double f = (E[i] - m[i]) - es;     // NaN m (NaN / inf anomaly) poisons d -> rejected
       const double a = ffma(-e, c[i], 1.0);
+#if RVLP_OPT & 2
+      const double ra = rcp64_40(a);           // 2^-40 on a step of ~1e-6; rinv below is re-derived against e cos E
+#else
       const double ra = rcp64(a);
+#endif
       const double x = f * ra;                 // Newton step, |x| <~ 1e-6
       const double y = es * ra;
+#if RVLP_OPT & 2
+      const double u = -0.5 * x;
+      const double d = x * ffma(u, y, -1.0);           // Halley: -x (1 + x y / 2), next term ~1e-19
+      const double h = u * x;                          // -d^2 / 2 to 2e-18: d = -x (1 + O(1e-6)), |h| ~ 1e-12
+#else
       const double d = -x * ffma(0.5 * x, y, 1.0);     // Halley: -x / (1 - x y / 2), next term ~1e-19
       const double h = -0.5 * (d * d);
+#endif
       const double sn = ffma(s[i], h, ffma(c[i], d, s[i]));
       const double cn = ffma(c[i], h, ffma(-s[i], d, c[i]));
       const double eps = ffma(ffma(e, cn, -1.0), ra, 1.0);   // 1 - (1 - e cos E) / a
@@ -481,7 +583,11 @@ RV_HD void kepler_stage_b(const StarterOut<W>& o, double e, int n64, double (&co
       const double u = ffma(-f, es, a2);
       const double v = (f * f) * (ec * RVK(19));
       const double den = ffma(a, u, v);
+#if RVLP_OPT & 2
+      const double d = -(f * t) * rcp64_3(den);
+#else
       const double d = -(f * t) * rcp64(den);
+#endif
       // rotate (s, c) by d:  sin d = d - d^3/6,  cos d - 1 = -d^2/2 + d^4/24
       const double d2 = d * d;
       double sd, cd1;
@@ -507,7 +613,11 @@ RV_HD void kepler_stage_b(const StarterOut<W>& o, double e, int n64, double (&co
   for (int i = 0; i < W; ++i) {
     cosE[i] = c[i];
     sinE[i] = xor_hi(s[i], sign[i]);
+#if RVLP_OPT & 2
+    rinv[i] = rcp64_3(ffma(-e, c[i], 1.0));
+#else
     rinv[i] = rcp64(ffma(-e, c[i], 1.0));
+#endif
   }
   }
 }
@@ -687,9 +797,22 @@ RV_HD void planet_rv_add(const PlanetConst& pc, const SolverPlan& plan, const do
   else if (plan.n64 == 1 && plan.n32 == 1) kepler_fast<W, 1, 1>(M, pc.e, 1, 1, cE, sE, dl, ri);
   else if (plan.n64 == 1 && plan.n32 == 2) kepler_fast<W, 2, 1>(M, pc.e, 2, 1, cE, sE, dl, ri);
   else kepler_fast<W>(M, pc.e, plan.n32, plan.n64, cE, sE, dl, ri);
+#if RVLP_OPT & 16
+  // one test per group: the largest |last step| and the largest |M| of the W anomalies, compared as high words
+  // (NaN / inf have the largest high words of all)
+  int dmax = 0, mmax = 0;
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    const int dh = hi32(dl[i]) & 0x7fffffff, mh = hi32(M[i]) & 0x7fffffff;
+    dmax = dh > dmax ? dh : dmax;
+    mmax = mh > mmax ? mh : mmax;
+  }
+  const bool bad = dmax >= hi32(plan.tol) || hi32(plan.tol) < 0 || mmax >= 0x4156e360;
+#else
   bool bad = false;
 #pragma unroll
   for (int i = 0; i < W; ++i) bad |= step_rejected(dl[i], plan.tol) || anomaly_is_big(M[i]);
+#endif
   if (RV_ANY(bad)) {                        // warp-uniform branch; rare
 #pragma unroll
     for (int i = 0; i < W; ++i) {
@@ -705,6 +828,40 @@ RV_HD void planet_rv_add(const PlanetConst& pc, const SolverPlan& plan, const do
   for (int i = 0; i < W; ++i) {
     // model.py:119-121, 170 with K, cos w, sin w folded into A, B, C (C == e A)
     const double u = ffma(-sE[i], pc.B, ffma(cE[i], pc.A, -pc.C));
+    rv[i] = ffma(ri[i], u, rv[i]);
+  }
+}
+
+// planet_rv_add for a planet known to take the lite plan (0 < e <= 0.65): same arithmetic, same bits, without the
+// circular-orbit test and the plan dispatch.
+template <int W>
+RV_HD void planet_rv_add_lite(double n, double tp, double e, double A, double B, double C, const double (&t)[W],
+                              double (&rv)[W]) {
+  double M[W], cE[W], sE[W], dl[W], ri[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) M[i] = mean_anomaly(n, t[i], tp);
+  kepler_fast<W, 1, 0>(M, e, 1, 0, cE, sE, dl, ri);
+  int dmax = 0, mmax = 0;
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    const int dh = hi32(dl[i]) & 0x7fffffff, mh = hi32(M[i]) & 0x7fffffff;
+    dmax = dh > dmax ? dh : dmax;
+    mmax = mh > mmax ? mh : mmax;
+  }
+  if (RV_ANY(dmax >= 0x3ed0c6f7 || mmax >= 0x4156e360)) {   // high words of the lite tolerance 4.0e-6 and of BIG_M
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      if (step_rejected(dl[i], 4.0e-6) || anomaly_is_big(M[i])) {
+        const CosSin cs = kepler_robust(M[i], e);
+        cE[i] = cs.c;
+        sE[i] = cs.s;
+        ri[i] = 1.0 / (1.0 - e * cs.c);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < W; ++i) {
+    const double u = ffma(-sE[i], B, ffma(cE[i], A, -C));
     rv[i] = ffma(ri[i], u, rv[i]);
   }
 }

@@ -12,12 +12,12 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 VDIR = os.path.join(ROOT, "build_variants")
 VARIANTS = {
-    "w4_mb2": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=2"],
-    "w4_t128_mb5": ["-DRVLP_W=4", "-DRVLP_MIN_BLOCKS=5", "-DRVLP_THREADS=128"],
-    "w3_mb3": ["-DRVLP_W=3", "-DRVLP_MIN_BLOCKS=3"],
-    "w3_t128_mb5": ["-DRVLP_W=3", "-DRVLP_MIN_BLOCKS=5", "-DRVLP_THREADS=128"],
-    "w5_mb2": ["-DRVLP_W=5", "-DRVLP_MIN_BLOCKS=2"],
-    "w5_t128_mb3": ["-DRVLP_W=5", "-DRVLP_MIN_BLOCKS=3", "-DRVLP_THREADS=128"],
+    "opt07": ["-DRVLP_OPT=7"],
+    "opt23": ["-DRVLP_OPT=23"],
+    "opt55": ["-DRVLP_OPT=55"],
+    "opt63": ["-DRVLP_OPT=63"],
+    "opt51": ["-DRVLP_OPT=51"],
+    "opt53": ["-DRVLP_OPT=53"],
 }
 
 CHILD = r"""
@@ -31,13 +31,19 @@ for name, maker, S in (("c3", workloads.make_c3, 200000), ("c4", workloads.make_
     spec, theta = maker(S)
     post = fit.from_spec(spec)
     th = torch.as_tensor(theta, device="cuda"); out = torch.empty(S, dtype=torch.float64, device="cuda")
-    for _ in range(3): post.ctx.logprob(th, out=out)
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(5): post.ctx.logprob(th, out=out)
-    b.record(); torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / 5
+    best = None
+    for v in (0, 1):
+        post.ctx.set_variant(v)
+        for _ in range(3): post.ctx.logprob(th, out=out)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5): post.ctx.logprob(th, out=out)
+        b.record(); torch.cuda.synchronize()
+        t = a.elapsed_time(b) / 5
+        res.setdefault(name + "_v", []).append(round(t, 3))
+        best = t if best is None else min(best, t)
+    ms = best
     units = S * len(spec["time"]) * len(spec["planet_letters"])
     ref = oracle_c.OracleProblem(spec).logprob(theta[:256])
     got = out[:256].cpu().numpy()
@@ -52,11 +58,17 @@ print("RESULT " + json.dumps(res))
 def build():
     os.makedirs(VDIR, exist_ok=True)
     src = os.path.join(ROOT, "ravest_b200", "csrc", "rvlp_capi.cu")
+    procs = []
+    for f in os.listdir(VDIR):
+        if f.endswith(".so"):
+            os.unlink(os.path.join(VDIR, f))
     for name, flags in VARIANTS.items():
         out = os.path.join(VDIR, f"lib_{name}.so")
         cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
                "-Xcompiler", "-fPIC", "-shared"] + flags + ["-o", out, src]
-        subprocess.run(cmd, check=True)
+        procs.append((out, subprocess.Popen(cmd)))
+    for out, p in procs:
+        assert p.wait() == 0, out
         print("built", out)
 
 
@@ -71,8 +83,8 @@ def run():
             print(f, "FAILED", r.stderr[-400:])
             continue
         res = json.loads(line[0][7:])
-        print(f, " ".join(f"{k}: {v['ms']:.3f} ms {v['Gunits_s']:.1f} G/s ok={v['parity_ok']}({v['err_over_tol']:.2g})"
-                          for k, v in res.items()), flush=True)
+        print(f, " ".join(f"{k}: {v['ms']:.3f} ms {v['Gunits_s']:.1f} G/s ok={v['parity_ok']}({v['err_over_tol']:.2g}) v0/v1={res[k + '_v']}"
+                          for k, v in res.items() if not k.endswith("_v")), flush=True)
 
 
 if __name__ == "__main__":
