@@ -17,6 +17,7 @@
 
 #include "rvlp_bands.cuh"
 #include "rvlp_gp.cuh"
+#include "rvlp_gp_big.cuh"
 #include "rvlp_gp_pipe.cuh"
 #include "rvlp_kernels.cuh"
 
@@ -96,6 +97,11 @@ int ensure_pool(int device) {
   return RVLP_OK;
 }
 
+bool gp_force_big() {
+  const char* which = getenv("RVLP_GP_KERNEL");   // tests: the big kernel as the second implementation at any N (read at
+  return which && !strcmp(which, "big");          // context creation)
+}
+
 int simple_grid(int64_t n) {
   int64_t g = (n + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
@@ -141,7 +147,8 @@ struct rvlp_ctx {
   void* d_src_const = nullptr;
   void* d_priors = nullptr;
   void* d_epochs = nullptr;
-  int smem_main = 0, smem_gp = 0, smem_gp_tiled = 0, smem_gp_blocked = 0, smem_gp_pipe = 0, smem_gp_pipe_pred = 0, gp_tile = 0, smem_gp_predict = 0;
+  int smem_main = 0, smem_gp_pipe = 0, smem_gp_pipe_pred = 0, gp_tile = 0;
+  int gp_big = 0, smem_gp_big = 0, smem_gp_big_pred = 0;   // N >= 220 epochs: rvlp_gp_big.cuh
   int max_smem = 0;
   int k1 = 0;          // K1 variant in use
   int k1_tuned = 0;    // rvlp_ctx_autotune has run
@@ -161,6 +168,52 @@ struct rvlp_ctx {
   cudaStream_t stream = nullptr;    // host-buffer path: chunks alternate between two streams so that
   cudaStream_t stream2 = nullptr;   // the H2D copy of chunk i+1 overlaps the kernel of chunk i
 };
+
+// Launch the blocked global-workspace kernel (rvlp_gp_big.cuh) for S samples: the workspace comes from the device's
+// stream-ordered pool for the duration of the launch; the grid is capped so that it stays below ~4 GB.
+template <bool PRED, int NW, int MB>
+static int launch_gp_big_shape(rvlp_ctx* c, const double* theta_dev, int64_t S, double* out_dev, double* beta_dev, cudaStream_t st) {
+  const int smem = PRED ? c->smem_gp_big_pred : c->smem_gp_big;
+  if (smem > c->max_smem)
+    return fail(RVLP_EUNSUPPORTED, "GP conditioning needs %d B of shared memory per CTA (> %d): too many epochs", smem, c->max_smem);
+  auto kern = gp_big_kernel<PRED, NW, MB>;
+  static std::atomic<uint64_t> attr_done{0};                // per device, as everywhere
+  if (c->device >= 64 || !((attr_done.load() >> c->device) & 1)) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    if (c->device < 64) attr_done.fetch_or(1ull << c->device);
+  }
+  int grid = 0;
+  int rc = grid_for(c->device, (const void*)kern, smem, S, &grid, 32 * NW);
+  if (rc) return rc;
+  const size_t per_cta = gp_big_ws_doubles(c->P.n_epochs) * sizeof(double);
+  const size_t cap = (size_t)4 << 30;
+  if ((size_t)grid * per_cta > cap) grid = (int)(cap / per_cta > 0 ? cap / per_cta : 1);
+  if (const char* e = getenv("RVLP_GP_GRID")) {             // tests / experiments: cap the grid
+    if (atoi(e) > 0 && atoi(e) < grid) grid = atoi(e);
+  }
+  if ((rc = ensure_pool(c->device))) return rc;
+  double* ws = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&ws, (size_t)grid * per_cta, st));
+  kern<<<grid, 32 * NW, smem, st>>>(c->P, theta_dev, S, out_dev, beta_dev, ws);
+  ++g_launches;
+  const cudaError_t le = cudaGetLastError();
+  cudaFreeAsync(ws, st);
+  if (le != cudaSuccess) return fail(RVLP_ECUDA, "gp_big_kernel launch failed: %s", cudaGetErrorString(le));
+  return RVLP_OK;
+}
+
+template <bool PRED>
+static int launch_gp_big(rvlp_ctx* c, const double* theta_dev, int64_t S, double* out_dev, double* beta_dev, cudaStream_t st) {
+  const char* e = getenv("RVLP_GP_BIG_SHAPE");              // experiments (tools/gp_big_time.py): warps per CTA x CTAs per SM
+  const int shape = e ? atoi(e) : 82;
+  switch (shape) {
+    case 44: return launch_gp_big_shape<PRED, 4, 4>(c, theta_dev, S, out_dev, beta_dev, st);
+    case 46: return launch_gp_big_shape<PRED, 4, 6>(c, theta_dev, S, out_dev, beta_dev, st);
+    case 83: return launch_gp_big_shape<PRED, 8, 3>(c, theta_dev, S, out_dev, beta_dev, st);
+    case 84: return launch_gp_big_shape<PRED, 8, 4>(c, theta_dev, S, out_dev, beta_dev, st);
+    default: return launch_gp_big_shape<PRED, 8, 2>(c, theta_dev, S, out_dev, beta_dev, st);
+  }
+}
 
 extern "C" {
 
@@ -254,6 +307,23 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
   P.priors = reinterpret_cast<const rvlp_prior*>(c->d_priors);
 
   CTX_TRY(cudaDeviceGetAttribute(&c->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  if (P.n_hyper) {
+    // GP contexts: the pipelined register-tile kernels up to 219 epochs, the blocked global-workspace kernel beyond
+    // (its CTAs read the epoch arrays from global memory: they do not fit next to anything else for thousands of epochs)
+    c->gp_tile = gp_tile_for(P.n_epochs);
+    if (c->gp_tile && gp_pipe_smem(P, smem_layout(P), c->gp_tile, true).total > c->max_smem) c->gp_tile = 0;
+    if (gp_force_big()) c->gp_tile = 0;
+    c->gp_big = c->gp_tile == 0;
+    if (c->gp_big) {
+      if (P.n_epochs > 16384) {
+        int rc = fail(RVLP_EUNSUPPORTED, "GP problems are limited to 16384 epochs (%d given): the dense factor needs "
+                      "%.1f GB per sample in flight", P.n_epochs, gp_big_ws_doubles(P.n_epochs) * 8e-9);
+        rvlp_ctx_destroy(c);
+        return rc;
+      }
+      P.epochs_global = 1;
+    }
+  }
   SmemLayout L = smem_layout(P);
   if (L.total > c->max_smem && !P.n_hyper) {   // too many epochs to stage per CTA: leave them in global memory
     P.epochs_global = 1;
@@ -271,34 +341,16 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
   CTX_TRY(cudaFuncSetAttribute(rv_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   CTX_TRY(cudaFuncSetAttribute(walker_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   if (P.n_hyper) {
-    c->smem_gp = gp_smem(P, L).total;
-    if (c->smem_gp > c->max_smem) {
-      int rc = fail(RVLP_EUNSUPPORTED, "GP problem needs %d B of shared memory per CTA (> %d)", c->smem_gp,
-                    c->max_smem);
-      rvlp_ctx_destroy(c);
-      return rc;
-    }
-    CTX_TRY(cudaFuncSetAttribute(gp_logprob_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-    CTX_TRY(cudaFuncSetAttribute(gp_predict_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-    c->smem_gp_predict = gp_predict_smem(P, L).total;
-    c->gp_tile = gp_tile_for(P.n_epochs);
-    c->smem_gp_tiled = gp_tiled_smem(P, L).total;
-    c->smem_gp_blocked = c->gp_tile ? gp_blocked_smem(P, L, c->gp_tile).total : 0;
     c->smem_gp_pipe = c->gp_tile ? gp_pipe_smem(P, L, c->gp_tile).total : 0;
     c->smem_gp_pipe_pred = c->gp_tile ? gp_pipe_smem(P, L, c->gp_tile, true).total : 0;
+    c->smem_gp_big = gp_big_smem(P, L, false).total;
+    c->smem_gp_big_pred = gp_big_smem(P, L, true).total;
 #define RVLP_GP_ATTR(TT)                                                                                                 \
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_pipe_kernel<TT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem)); \
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_pipe_kernel<TT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     RVLP_GP_ATTR(2) RVLP_GP_ATTR(4) RVLP_GP_ATTR(6) RVLP_GP_ATTR(8) RVLP_GP_ATTR(10)
 #undef RVLP_GP_ATTR
-    CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-    CTX_TRY(cudaFuncSetAttribute(gp_logprob_blocked_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-    CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-    CTX_TRY(cudaFuncSetAttribute(gp_logprob_blocked_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-    CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-    CTX_TRY(cudaFuncSetAttribute(gp_logprob_blocked_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-    CTX_TRY(cudaFuncSetAttribute(gp_logprob_tiled_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
-    CTX_TRY(cudaFuncSetAttribute(gp_logprob_blocked_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CTX_TRY(cudaFuncSetAttribute(gp_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   }
   CTX_TRY(cudaMalloc((void**)&c->d_tickets, sizeof(unsigned long long) * kTicketRing));
   for (int i = 0; i < kTicketRing; ++i) CTX_TRY(cudaEventCreateWithFlags(&c->ticket_ev[i], cudaEventDisableTiming));
@@ -646,54 +698,22 @@ int rvlp_gp_logprob_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
   if (c->P.n_hyper != 4) return fail(RVLP_EINVAL, "context was not created with GP hyperparameters");
   if (S == 0) return RVLP_OK;
   DeviceGuard guard(c->device);
-  int grid = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  int rc;
-  // The software-pipelined register-tile kernel (rvlp_gp_pipe.cuh) is the product path for N <= 175 epochs.
-  // RVLP_GP_KERNEL=smem|column|blocked selects the older lock-step kernels (kept for cross-checks in the tests).
-  const char* which = getenv("RVLP_GP_KERNEL");
-  const bool use_smem = which && !strcmp(which, "smem");
-  bool use_column = false, use_pipe = !(which && *which) || !strcmp(which, "pipe");
-  if (which && !strcmp(which, "column")) use_column = true;
-  const char* grid_cap = getenv("RVLP_GP_GRID");          // experiments: cap the grid (e.g. 148 = one CTA per SM)
-#define RVLP_GP_TILED(TT)                                                                                   \
+  if (c->gp_big) return launch_gp_big<false>(c, theta_dev, S, out_dev, nullptr, st);
+  int grid = 0, rc;
+  const char* grid_cap = getenv("RVLP_GP_GRID");          // tests / experiments: cap the grid (e.g. 148 = one CTA per SM)
+#define RVLP_GP_PIPE(TT)                                                                                    \
   case TT:                                                                                                  \
-    if (use_pipe) {                                                                                         \
-      rc = grid_for(c->device, (const void*)gp_logprob_pipe_kernel<TT, false>, c->smem_gp_pipe, S, &grid);  \
-      if (rc) return rc;                                                                                    \
-      if (grid_cap && atoi(grid_cap) > 0 && atoi(grid_cap) < grid) grid = atoi(grid_cap);                   \
-      gp_logprob_pipe_kernel<TT, false><<<grid, kThreads, c->smem_gp_pipe, st>>>(c->P, theta_dev, S, out_dev, nullptr); \
-    } else if (use_column) {                                                                                \
-      rc = grid_for(c->device, (const void*)gp_logprob_tiled_kernel<TT>, c->smem_gp_tiled, S, &grid);       \
-      if (rc) return rc;                                                                                    \
-      gp_logprob_tiled_kernel<TT><<<grid, kThreads, c->smem_gp_tiled, st>>>(c->P, theta_dev, S, out_dev);   \
-    } else {                                                                                                \
-      rc = grid_for(c->device, (const void*)gp_logprob_blocked_kernel<TT>, c->smem_gp_blocked, S, &grid);   \
-      if (rc) return rc;                                                                                    \
-      if (grid_cap && atoi(grid_cap) > 0 && atoi(grid_cap) < grid) grid = atoi(grid_cap);                   \
-      gp_logprob_blocked_kernel<TT><<<grid, kThreads, c->smem_gp_blocked, st>>>(c->P, theta_dev, S, out_dev); \
-    }                                                                                                       \
+    rc = grid_for(c->device, (const void*)gp_logprob_pipe_kernel<TT, false>, c->smem_gp_pipe, S, &grid);    \
+    if (rc) return rc;                                                                                      \
+    if (grid_cap && atoi(grid_cap) > 0 && atoi(grid_cap) < grid) grid = atoi(grid_cap);                     \
+    gp_logprob_pipe_kernel<TT, false><<<grid, kThreads, c->smem_gp_pipe, st>>>(c->P, theta_dev, S, out_dev, nullptr); \
     break;
-  switch (use_smem ? 0 : c->gp_tile) {
-    RVLP_GP_TILED(2)
-    RVLP_GP_TILED(4)
-    RVLP_GP_TILED(6)
-    RVLP_GP_TILED(8)
-    case 10:   // 176 .. 219 epochs: 10 x 10 register tiles exist for the pipelined kernel only
-      if (use_pipe && c->smem_gp_pipe <= c->max_smem) {
-        rc = grid_for(c->device, (const void*)gp_logprob_pipe_kernel<10, false>, c->smem_gp_pipe, S, &grid);
-        if (rc) return rc;
-        if (grid_cap && atoi(grid_cap) > 0 && atoi(grid_cap) < grid) grid = atoi(grid_cap);
-        gp_logprob_pipe_kernel<10, false><<<grid, kThreads, c->smem_gp_pipe, st>>>(c->P, theta_dev, S, out_dev, nullptr);
-        break;
-      }
-      // fall through
-    default:   // more epochs (or RVLP_GP_KERNEL=smem|column|blocked): shared-memory right-looking kernel
-      rc = grid_for(c->device, (const void*)gp_logprob_kernel, c->smem_gp, S, &grid);
-      if (rc) return rc;
-      gp_logprob_kernel<<<grid, kThreads, c->smem_gp, st>>>(c->P, theta_dev, S, out_dev);
+  switch (c->gp_tile) {
+    RVLP_GP_PIPE(2) RVLP_GP_PIPE(4) RVLP_GP_PIPE(6) RVLP_GP_PIPE(8) RVLP_GP_PIPE(10)
+    default: return fail(RVLP_EUNSUPPORTED, "no GP tile size for %d epochs", c->P.n_epochs);
   }
-#undef RVLP_GP_TILED
+#undef RVLP_GP_PIPE
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return RVLP_OK;
@@ -723,25 +743,25 @@ int rvlp_gp_predict_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const
   if (c->P.n_hyper != 4) return fail(RVLP_EINVAL, "context was not created with GP hyperparameters");
   if (T > 0 && (!times_dev || !mean_dev)) return fail(RVLP_EINVAL, "null times / mean pointer");
   if (S == 0 || (T == 0 && !chi2_dev)) return RVLP_OK;
-  // Product path for N <= 175 epochs: the pipelined register-tile factorisation with the factor kept in shared memory
-  // and a blocked back substitution (beta = C^-1 r into a context-owned scratch), then the conditional-mean kernel.
-  // RVLP_GP_KERNEL=smem selects the older single kernel (cross-checks).
-  const char* which = getenv("RVLP_GP_KERNEL");
-  if (c->gp_tile && c->smem_gp_pipe_pred <= c->max_smem && !(which && !strcmp(which, "smem"))) {
-    DeviceGuard guard(c->device);
-    cudaStream_t st = (cudaStream_t)stream;
-    const int N = c->P.n_epochs;
-    // beta = C^-1 r scratch [S, N]: allocated per call from the device's stream-ordered pool (no host sync in steady
-    // state once the pool has grown; concurrent calls on different streams never share it) and released on `st` after
-    // the mean kernel.
-    if (int prc = ensure_pool(c->device)) return prc;
-    double* d_beta = nullptr;
-    CUDA_TRY(cudaMallocAsync((void**)&d_beta, sizeof(double) * (size_t)S * N, st));
-    struct BetaFree {
-      double* p; cudaStream_t st;
-      ~BetaFree() { cudaFreeAsync(p, st); }
-    } beta_free{d_beta, st};
-    int grid = 0, rc = RVLP_OK;
+  // N <= 219 epochs: the pipelined register-tile factorisation with the factor kept in shared memory and a blocked back
+  // substitution; more epochs: the blocked global-workspace kernel.  Either writes beta = C^-1 r into a per-call
+  // scratch; the conditional-mean kernel follows.
+  DeviceGuard guard(c->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = c->P.n_epochs;
+  // beta scratch [S, N]: allocated per call from the device's stream-ordered pool (no host sync in steady state once
+  // the pool has grown; concurrent calls on different streams never share it), released on `st` after the mean kernel.
+  if (int prc = ensure_pool(c->device)) return prc;
+  double* d_beta = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&d_beta, sizeof(double) * (size_t)S * N, st));
+  struct BetaFree {
+    double* p; cudaStream_t st;
+    ~BetaFree() { cudaFreeAsync(p, st); }
+  } beta_free{d_beta, st};
+  int grid = 0, rc = RVLP_OK;
+  if (c->gp_big) {
+    if ((rc = launch_gp_big<true>(c, theta_dev, S, chi2_dev, d_beta, st))) return rc;
+  } else {
     const char* grid_cap = getenv("RVLP_GP_GRID");        // tests / experiments: cap the grid
 #define RVLP_GP_PRED(TT)                                                                                          \
   case TT:                                                                                                        \
@@ -757,27 +777,18 @@ int rvlp_gp_predict_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const
 #undef RVLP_GP_PRED
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
-    if (T > 0) {
-      const int smem_mean = 4 * ((N + 1) & ~1) * 8;
-      rc = grid_for(c->device, (const void*)gp_mean_kernel, smem_mean, S, &grid);
-      if (rc) return rc;
-      gp_mean_kernel<<<grid, kThreads, smem_mean, st>>>(c->P, theta_dev, S, d_beta, times_dev, T, mean_dev);
-      ++g_launches;
-      CUDA_TRY(cudaGetLastError());
-    }
-    return RVLP_OK;
   }
-  if (c->smem_gp_predict > c->max_smem)
-    return fail(RVLP_EUNSUPPORTED, "GP conditioning needs %d B of shared memory per CTA (> %d): too many epochs",
-                c->smem_gp_predict, c->max_smem);
-  DeviceGuard guard(c->device);
-  int grid = 0;
-  int rc = grid_for(c->device, (const void*)gp_predict_kernel, c->smem_gp_predict, S, &grid);
-  if (rc) return rc;
-  gp_predict_kernel<<<grid, kThreads, c->smem_gp_predict, (cudaStream_t)stream>>>(c->P, theta_dev, S, times_dev, T,
-                                                                                  mean_dev, chi2_dev);
-  ++g_launches;
-  CUDA_TRY(cudaGetLastError());
+  if (T > 0) {
+    const int smem_mean = 4 * ((N + 1) & ~1) * 8;
+    if (smem_mean > c->max_smem)
+      return fail(RVLP_EUNSUPPORTED, "GP conditional mean needs %d B of shared memory per CTA (> %d): too many epochs",
+                  smem_mean, c->max_smem);
+    rc = grid_for(c->device, (const void*)gp_mean_kernel, smem_mean, S, &grid);
+    if (rc) return rc;
+    gp_mean_kernel<<<grid, kThreads, smem_mean, st>>>(c->P, theta_dev, S, d_beta, times_dev, T, mean_dev);
+    ++g_launches;
+    CUDA_TRY(cudaGetLastError());
+  }
   return RVLP_OK;
 }
 
