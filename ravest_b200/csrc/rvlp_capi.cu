@@ -17,7 +17,7 @@
 
 #include "rvlp_bands.cuh"
 #include "rvlp_gp.cuh"
-#include "rvlp_gp_big.cuh"
+#include "rvlp_gp_batch.cuh"
 #include "rvlp_gp_pipe.cuh"
 #include "rvlp_kernels.cuh"
 
@@ -97,11 +97,6 @@ int ensure_pool(int device) {
   return RVLP_OK;
 }
 
-bool gp_force_big() {
-  const char* which = getenv("RVLP_GP_KERNEL");   // tests: the big kernel as the second implementation at any N (read at
-  return which && !strcmp(which, "big");          // context creation)
-}
-
 int simple_grid(int64_t n) {
   int64_t g = (n + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
@@ -148,7 +143,6 @@ struct rvlp_ctx {
   void* d_priors = nullptr;
   void* d_epochs = nullptr;
   int smem_main = 0, smem_gp_pipe = 0, smem_gp_pipe_pred = 0, gp_tile = 0;
-  int gp_big = 0, smem_gp_big = 0, smem_gp_big_pred = 0;   // N >= 220 epochs: rvlp_gp_big.cuh
   int max_smem = 0;
   int k1 = 0;          // K1 variant in use
   int k1_tuned = 0;    // rvlp_ctx_autotune has run
@@ -169,50 +163,103 @@ struct rvlp_ctx {
   cudaStream_t stream2 = nullptr;   // the H2D copy of chunk i+1 overlaps the kernel of chunk i
 };
 
-// Launch the blocked global-workspace kernel (rvlp_gp_big.cuh) for S samples: the workspace comes from the device's
-// stream-ordered pool for the duration of the launch; the grid is capped so that it stays below ~4 GB.
-template <bool PRED, int NW, int MB>
-static int launch_gp_big_shape(rvlp_ctx* c, const double* theta_dev, int64_t S, double* out_dev, double* beta_dev, cudaStream_t st) {
-  const int smem = PRED ? c->smem_gp_big_pred : c->smem_gp_big;
-  if (smem > c->max_smem)
-    return fail(RVLP_EUNSUPPORTED, "GP conditioning needs %d B of shared memory per CTA (> %d): too many epochs", smem, c->max_smem);
-  auto kern = gp_big_kernel<PRED, NW, MB>;
-  static std::atomic<uint64_t> attr_done{0};                // per device, as everywhere
+// Level-synchronous batched Cholesky (rvlp_gp_batch.cuh): one kernel per block column over ALL samples of a chunk.
+// The per-sample factors live in a workspace from the device's stream-ordered pool (chunks of at most ~6 GB).
+template <bool PRED>
+static int launch_gp_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, double* out_dev, double* beta_dev, cudaStream_t st) {
+  DevProblem P = c->P;
+  P.epochs_global = 1;                                      // these kernels read the epoch arrays through L1
+  const int N = P.n_epochs;
+  const GpbDims d = gpb_dims(N);
+  const size_t per = (gpb_bytes_per_sample(N, P.n_inst) + 255) & ~(size_t)255;
+  size_t cap = (size_t)6 << 30;
+  if (const char* e = getenv("RVLP_GP_BATCH_MB")) {         // tests: force chunking
+    if (atoi(e) > 0) cap = (size_t)atoi(e) << 20;
+  }
+  int64_t chunk = (int64_t)(cap / per);
+  if (chunk < 1) chunk = 1;
+  if (chunk > S) chunk = S;
+  int rc = ensure_pool(c->device);
+  if (rc) return rc;
+  static std::atomic<uint64_t> attr_done{0};                // per device
   if (c->device >= 64 || !((attr_done.load() >> c->device) & 1)) {
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(gpb_prologue_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(gpb_prologue_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CUDA_TRY(cudaFuncSetAttribute(gpb_backsub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
     if (c->device < 64) attr_done.fetch_or(1ull << c->device);
   }
-  int grid = 0;
-  int rc = grid_for(c->device, (const void*)kern, smem, S, &grid, 32 * NW);
-  if (rc) return rc;
-  const size_t per_cta = gp_big_ws_doubles(c->P.n_epochs) * sizeof(double);
-  const size_t cap = (size_t)4 << 30;
-  if ((size_t)grid * per_cta > cap) grid = (int)(cap / per_cta > 0 ? cap / per_cta : 1);
-  if (const char* e = getenv("RVLP_GP_GRID")) {             // tests / experiments: cap the grid
-    if (atoi(e) > 0 && atoi(e) < grid) grid = atoi(e);
+  const int smem_pro = smem_layout(P).total;
+  if (smem_pro > c->max_smem || N * 8 > c->max_smem)
+    return fail(RVLP_EUNSUPPORTED, "GP problem needs %d B of shared memory per CTA (> %d)", smem_pro > N * 8 ? smem_pro : N * 8, c->max_smem);
+  unsigned char* slab = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&slab, (size_t)chunk * per + 8192, st));
+  struct SlabFree {
+    void* p; cudaStream_t st;
+    ~SlabFree() { cudaFreeAsync(p, st); }
+  } slab_free{slab, st};
+  GpbWork w;
+  {
+    unsigned char* o = slab;
+    auto take = [&](size_t bytes) { unsigned char* r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    w.L = (double*)take((size_t)chunk * d.nblk * 256 * 8);
+    w.invd = (double*)take((size_t)chunk * d.np * 8);
+    w.resid = (double*)take((size_t)chunk * d.np * 8);
+    w.cph = (double*)take((size_t)chunk * d.np * 8);
+    w.sph = (double*)take((size_t)chunk * d.np * 8);
+    w.hyp = (double*)take((size_t)chunk * 4 * 8);
+    w.jit2 = (double*)take((size_t)chunk * P.n_inst * 8);
+    w.lp = (double*)take((size_t)chunk * 8);
+    w.lhp = (double*)take((size_t)chunk * 8);
+    w.chi2 = (double*)take((size_t)chunk * 8);
+    w.logdet = (double*)take((size_t)chunk * 8);
+    w.status = (int*)take((size_t)chunk * 4);
+    if ((size_t)(o - slab) > (size_t)chunk * per + 8192) return fail(RVLP_ECUDA, "internal: GP workspace carve overflow");
   }
-  if ((rc = ensure_pool(c->device))) return rc;
-  double* ws = nullptr;
-  CUDA_TRY(cudaMallocAsync((void**)&ws, (size_t)grid * per_cta, st));
-  kern<<<grid, 32 * NW, smem, st>>>(c->P, theta_dev, S, out_dev, beta_dev, ws);
-  ++g_launches;
-  const cudaError_t le = cudaGetLastError();
-  cudaFreeAsync(ws, st);
-  if (le != cudaSuccess) return fail(RVLP_ECUDA, "gp_big_kernel launch failed: %s", cudaGetErrorString(le));
+  int sms = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+  for (int64_t s0 = 0; s0 < S; s0 += chunk) {
+    const int64_t n = S - s0 < chunk ? S - s0 : chunk;
+    const double* th = theta_dev + s0 * P.ndim;
+    int grid = 0;
+    if ((rc = grid_for(c->device, (const void*)gpb_prologue_kernel<PRED>, smem_pro, (n + kWarps - 1) / kWarps, &grid))) return rc;
+    gpb_prologue_kernel<PRED><<<grid, kThreads, smem_pro, st>>>(P, th, n, w);
+    if ((rc = grid_for(c->device, (const void*)gpb_diag0_kernel, 0, (n + kGbWarps - 1) / kGbWarps, &grid, kGbThreads))) return rc;
+    gpb_diag0_kernel<<<grid, kGbThreads, 0, st>>>(P, n, w);
+    g_launches += 2;
+    for (int J = 0; J + 1 < d.nbr; ++J) {
+      const int64_t tasks = n * (int64_t)(d.nbr - 1 - J);       // one warp per (sample, row block below the diagonal)
+      if ((rc = grid_for(c->device, (const void*)gpb_step_kernel, 0, (tasks + kGbWarps - 1) / kGbWarps, &grid, kGbThreads))) return rc;
+      gpb_step_kernel<<<grid, kGbThreads, 0, st>>>(P, n, w, J);
+      ++g_launches;
+    }
+    int64_t gf = (n + 127) / 128;
+    if (gf > sms * 8) gf = sms * 8;
+    gpb_finish_kernel<PRED><<<(int)gf, 128, 0, st>>>(P, n, w, out_dev ? out_dev + s0 : nullptr, beta_dev ? beta_dev + s0 * N : nullptr);
+    ++g_launches;
+    if (PRED) {
+      if ((rc = grid_for(c->device, (const void*)gpb_backsub_kernel, N * 8, n, &grid, kGbThreads))) return rc;
+      gpb_backsub_kernel<<<grid, kGbThreads, N * 8, st>>>(P, n, w, beta_dev + s0 * N);
+      ++g_launches;
+    }
+    CUDA_TRY(cudaGetLastError());
+  }
   return RVLP_OK;
 }
 
-template <bool PRED>
-static int launch_gp_big(rvlp_ctx* c, const double* theta_dev, int64_t S, double* out_dev, double* beta_dev, cudaStream_t st) {
-  const char* e = getenv("RVLP_GP_BIG_SHAPE");              // experiments (tools/gp_big_time.py): warps per CTA x CTAs per SM
-  const int shape = e ? atoi(e) : 82;
-  switch (shape) {
-    case 44: return launch_gp_big_shape<PRED, 4, 4>(c, theta_dev, S, out_dev, beta_dev, st);
-    case 46: return launch_gp_big_shape<PRED, 4, 6>(c, theta_dev, S, out_dev, beta_dev, st);
-    case 83: return launch_gp_big_shape<PRED, 8, 3>(c, theta_dev, S, out_dev, beta_dev, st);
-    case 84: return launch_gp_big_shape<PRED, 8, 4>(c, theta_dev, S, out_dev, beta_dev, st);
-    default: return launch_gp_big_shape<PRED, 8, 2>(c, theta_dev, S, out_dev, beta_dev, st);
+// Which GP implementation serves a call.  N >= 220: the batched path always (the pipelined kernels do not exist there).
+// N <= 219: the pipelined one-CTA-per-sample kernel for small batches (one launch, ~50 us latency) and for
+// 81..149 epochs; the batched path from 2048 samples on where it measured faster (profiles/r02_gp_kernels_time.log:
+// N = 30: 0.26 vs 0.37 ms per 2e4, N = 57: 0.76 vs 0.81, N = 120: 1.53 vs 1.46 per 1e4, N = 200: 1.90 vs 3.15 per 4e3).
+// RVLP_GP_KERNEL = pipe | batch forces one (tests, experiments).
+enum { GP_PIPE = 0, GP_BATCH = 2 };
+static int gp_choice(const rvlp_ctx* c, int64_t S) {
+  if (c->gp_tile == 0) return GP_BATCH;
+  if (const char* e = getenv("RVLP_GP_KERNEL")) {
+    if (!strcmp(e, "batch")) return GP_BATCH;
+    if (!strcmp(e, "pipe")) return GP_PIPE;
   }
+  const int N = c->P.n_epochs;
+  return (S >= 2048 && (N <= 80 || N >= 150)) ? GP_BATCH : GP_PIPE;
 }
 
 extern "C" {
@@ -308,21 +355,17 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
 
   CTX_TRY(cudaDeviceGetAttribute(&c->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   if (P.n_hyper) {
-    // GP contexts: the pipelined register-tile kernels up to 219 epochs, the blocked global-workspace kernel beyond
-    // (its CTAs read the epoch arrays from global memory: they do not fit next to anything else for thousands of epochs)
+    // GP contexts: the pipelined register-tile kernels up to 219 epochs; the level-synchronous batched path
+    // (rvlp_gp_batch.cuh, factors in a global workspace) for any epoch count up to 16384
     c->gp_tile = gp_tile_for(P.n_epochs);
     if (c->gp_tile && gp_pipe_smem(P, smem_layout(P), c->gp_tile, true).total > c->max_smem) c->gp_tile = 0;
-    if (gp_force_big()) c->gp_tile = 0;
-    c->gp_big = c->gp_tile == 0;
-    if (c->gp_big) {
-      if (P.n_epochs > 16384) {
-        int rc = fail(RVLP_EUNSUPPORTED, "GP problems are limited to 16384 epochs (%d given): the dense factor needs "
-                      "%.1f GB per sample in flight", P.n_epochs, gp_big_ws_doubles(P.n_epochs) * 8e-9);
-        rvlp_ctx_destroy(c);
-        return rc;
-      }
-      P.epochs_global = 1;
+    if (P.n_epochs > 16384) {
+      int rc = fail(RVLP_EUNSUPPORTED, "GP problems are limited to 16384 epochs (%d given): the dense factor needs "
+                    "%.1f GB per sample in flight", P.n_epochs, gpb_bytes_per_sample(P.n_epochs, P.n_inst) * 1e-9);
+      rvlp_ctx_destroy(c);
+      return rc;
     }
+    if (c->gp_tile == 0) P.epochs_global = 1;   // no kernel of this context stages the epochs in shared memory
   }
   SmemLayout L = smem_layout(P);
   if (L.total > c->max_smem && !P.n_hyper) {   // too many epochs to stage per CTA: leave them in global memory
@@ -343,8 +386,6 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
   if (P.n_hyper) {
     c->smem_gp_pipe = c->gp_tile ? gp_pipe_smem(P, L, c->gp_tile).total : 0;
     c->smem_gp_pipe_pred = c->gp_tile ? gp_pipe_smem(P, L, c->gp_tile, true).total : 0;
-    c->smem_gp_big = gp_big_smem(P, L, false).total;
-    c->smem_gp_big_pred = gp_big_smem(P, L, true).total;
 #define RVLP_GP_ATTR(TT)                                                                                                 \
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_pipe_kernel<TT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem)); \
     CTX_TRY(cudaFuncSetAttribute(gp_logprob_pipe_kernel<TT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
@@ -699,7 +740,8 @@ int rvlp_gp_logprob_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
   if (S == 0) return RVLP_OK;
   DeviceGuard guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
-  if (c->gp_big) return launch_gp_big<false>(c, theta_dev, S, out_dev, nullptr, st);
+  const int which = gp_choice(c, S);
+  if (which == GP_BATCH) return launch_gp_batch<false>(c, theta_dev, S, out_dev, nullptr, st);
   int grid = 0, rc;
   const char* grid_cap = getenv("RVLP_GP_GRID");          // tests / experiments: cap the grid (e.g. 148 = one CTA per SM)
 #define RVLP_GP_PIPE(TT)                                                                                    \
@@ -759,8 +801,9 @@ int rvlp_gp_predict_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const
     ~BetaFree() { cudaFreeAsync(p, st); }
   } beta_free{d_beta, st};
   int grid = 0, rc = RVLP_OK;
-  if (c->gp_big) {
-    if ((rc = launch_gp_big<true>(c, theta_dev, S, chi2_dev, d_beta, st))) return rc;
+  const int which = gp_choice(c, S);
+  if (which == GP_BATCH) {
+    if ((rc = launch_gp_batch<true>(c, theta_dev, S, chi2_dev, d_beta, st))) return rc;
   } else {
     const char* grid_cap = getenv("RVLP_GP_GRID");        // tests / experiments: cap the grid
 #define RVLP_GP_PRED(TT)                                                                                          \

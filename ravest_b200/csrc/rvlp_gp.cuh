@@ -8,10 +8,13 @@
 //   C = L L^T,  alpha = L^-1 (v - mean),  ll = -1/2 alpha.alpha - sum log L_ii - N/2 log 2 pi.
 //
 // This header holds what the GP kernels share.  The kernels themselves:
-//   rvlp_gp_pipe.cuh  N <= 219 epochs: software-pipelined register-tile Cholesky, factor in shared memory (K3, K7)
-//   rvlp_gp_big.cuh   N >= 220 epochs: blocked left-looking Cholesky in a global workspace, DMMA trailing updates
-// (The lock-step shared-memory / column / blocked predecessors of round 1 were removed in round 2: the big kernel runs
-// at any N and serves as the independent second implementation in the tests, `RVLP_GP_KERNEL=big`.)
+//   rvlp_gp_pipe.cuh   N <= 219 epochs: one CTA per sample, software-pipelined register-tile Cholesky, factor in shared
+//                      memory (K3, K7) - small batches, and 81..149 epochs
+//   rvlp_gp_batch.cuh  any N <= 16384: level-synchronous batched Cholesky, one kernel per block column over all samples,
+//                      16 x 16 blocks in a global workspace, DMMA (fp64 tensor core) Gram sums
+// (The lock-step shared-memory / column / blocked predecessors of round 1 and a one-CTA-per-sample global-workspace
+// kernel tried in round 2 were removed; each path is the other's independent second implementation in the tests,
+// `RVLP_GP_KERNEL=pipe|batch`.)
 #pragma once
 #include "rvlp_kernels.cuh"
 #include "rvlp_gpcov.cuh"
@@ -30,6 +33,14 @@ __device__ __forceinline__ double pivot_rsqrt(double x) {
   e = fma(-hx * y, y, 0.5);
   y = fma(y, e, y);
   return y;
+}
+
+// D(8x8) += A(8x4) B(4x8), fp64 tensor-core MMA.  Fragments (PTX ISA, m8n8k4 .f64): a = A[lane / 4][lane % 4],
+// b = B[lane % 4][lane / 4], {c0, c1} = C[lane / 4][2 (lane % 4) + {0, 1}].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
 }
 
 // Register-tile size of the pipelined kernels for a given epoch count: 22 tile rows of TT epochs (incl. the residual

@@ -536,13 +536,15 @@ def test_gp_epoch_limit_is_a_clean_error(cuda):
         _post(spec).log_probability_batch(theta)
 
 
+@pytest.mark.parametrize("kernel", ["batch"])
 @pytest.mark.parametrize("N,S", [(220, 40), (231, 24), (256, 40), (300, 24), (512, 24), (700, 12), (1000, 8)])
-def test_gp_many_epochs_blocked_dmma_kernel(cuda, N, S):
-    """N >= 220 (rvlp_gp_big.cuh: left-looking blocked Cholesky, DMMA trailing updates, global workspace): log-posterior
+def test_gp_many_epochs_blocked_dmma_kernel(cuda, monkeypatch, N, S, kernel):
+    """N >= 220 (rvlp_gp_batch.cuh: level-synchronous batched Cholesky, DMMA Gram sums, global workspace): log-posterior
     against the C restatement, conditional mean + chi^2 against the numpy restatement (both pinned to scikit-learn by
     tests/test_oracle.py), NaN / -inf rows, bit-stability under the grid size and the row order."""
     from oracle import oracle_c, oracle_py
     from ravest_b200 import workloads
+    monkeypatch.setenv("RVLP_GP_KERNEL", kernel)
     spec, theta = workloads.make_c5(n_samples=S, n_planets=1 + (N % 2), n_epochs=N, seed=3000 + N)
     names = workloads.free_names(spec) + list(spec["hyperparams"])
     theta[3, names.index("gp_amp")] = -1.0                 # rejected row
@@ -569,14 +571,16 @@ def test_gp_many_epochs_blocked_dmma_kernel(cuda, N, S):
         mu, c2 = pr.gp_predict(dict(zip(names, map(float, theta[i]))), times)
         assert np.abs(mean[i] - mu).max() <= 1e-7 * max(1.0, np.abs(mu).max()), (N, i)
         assert abs(chi2[i] - c2) <= 1e-9 * max(1.0, c2), (N, i)
-    # bits do not depend on the grid or on the row order
-    import os
-    os.environ["RVLP_GP_GRID"] = "3"
-    try:
-        again = post.log_probability_batch(th).cpu().numpy()
-    finally:
-        del os.environ["RVLP_GP_GRID"]
+    # bits do not depend on the grid / the chunking of the batch, nor on the row order
+    monkeypatch.setenv("RVLP_GP_GRID", "3")
+    monkeypatch.setenv("RVLP_GP_BATCH_MB", "8")          # batched path: a few samples per chunk
+    again = post.log_probability_batch(th).cpu().numpy()
+    mean2, chi22 = post.ctx.gp_predict(th, times, want_chi2=True)
+    monkeypatch.delenv("RVLP_GP_GRID")
+    monkeypatch.delenv("RVLP_GP_BATCH_MB")
     assert np.array_equal(again.view(np.int64), got.view(np.int64))
+    assert np.array_equal(mean2.cpu().numpy().view(np.int64), mean.view(np.int64))
+    assert np.array_equal(chi22.cpu().numpy().view(np.int64), chi2.view(np.int64))
     perm = np.random.default_rng(1).permutation(S)
     shuffled = post.log_probability_batch(cuda.as_tensor(theta[perm], device="cuda")).cpu().numpy()
     assert np.array_equal(shuffled.view(np.int64), got[perm].view(np.int64))
@@ -629,16 +633,16 @@ def test_gp_against_restatement(cuda):
     assert abs(post.log_probability(x) - got[5]) == 0.0
 
 
-@pytest.mark.parametrize("kernel", ["pipe", "big"])
+@pytest.mark.parametrize("kernel", ["pipe", "batch"])
 def test_gp_against_sklearn_fixtures(cuda, monkeypatch, kernel):
-    """(kernel = "big": the N >= 220 DMMA kernel forced onto the same small problems, RVLP_GP_KERNEL=big.)
+    """(kernel = "batch": the level-synchronous batched DMMA path forced onto the same small problems, RVLP_GP_KERNEL.)
     Rows a17, a18, f-4 against an implementation the builder did not write: tests/golden/gp_sklearn.json holds
     scikit-learn's log marginal likelihood, conditional mean and y^T C^-1 y for the same kernel
     (tests/golden/make_gp_sklearn.py).  Log-probability to the north_star's 1e-7 absolute (+ 1e-11 relative for the
     conditioning of the solve), mean to 1e-8 of its scale, chi^2 to 1e-9 relative."""
     from ravest_b200 import workloads
-    if kernel == "big":
-        monkeypatch.setenv("RVLP_GP_KERNEL", "big")
+    if kernel != "pipe":
+        monkeypatch.setenv("RVLP_GP_KERNEL", kernel)
     g = load_golden("gp_sklearn")
     n = 0
     for c in g["cases"]:
@@ -666,9 +670,9 @@ def test_gp_against_sklearn_fixtures(cuda, monkeypatch, kernel):
 
 
 @pytest.mark.parametrize("N", [1, 2, 7, 43, 44, 87, 88, 131, 132, 175, 176, 200, 219, 220, 228])
-def test_gp_every_tile_size_and_the_blocked_kernel(cuda, N, monkeypatch):
-    """Register-tiled pipelined Cholesky at each tile size boundary (T = 2/4/6/8/10, N <= 219), the blocked DMMA kernel
-    above that, and the blocked kernel forced onto every N against the same oracle."""
+def test_gp_every_tile_size_and_the_batched_path(cuda, N, monkeypatch):
+    """Register-tiled pipelined Cholesky at each tile size boundary (T = 2/4/6/8/10, N <= 219), the batched DMMA path
+    above that, and the batched path forced onto every N against the same oracle."""
     from oracle import oracle_c
     from ravest_b200 import workloads
     spec, theta = workloads.make_c5(n_samples=48, n_planets=1, n_epochs=N, seed=600 + N)
@@ -678,10 +682,11 @@ def test_gp_every_tile_size_and_the_blocked_kernel(cuda, N, monkeypatch):
     fin = np.isfinite(ref)
     assert fin.sum() > 30
     assert np.all(np.abs(got[fin] - ref[fin]) <= 1e-7 + 1e-11 * np.abs(ref[fin])), np.abs(got[fin] - ref[fin]).max()
-    monkeypatch.setenv("RVLP_GP_KERNEL", "big")   # the second implementation (rvlp_gp_big.cuh) against the same oracle
-    alt = _post(spec).log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
-    assert np.array_equal(np.isneginf(alt), np.isneginf(ref))
-    assert np.all(np.abs(alt[fin] - ref[fin]) <= 1e-7 + 1e-11 * np.abs(ref[fin])), "big"
+    for which in ("batch"):                 # the other two implementations against the same oracle
+        monkeypatch.setenv("RVLP_GP_KERNEL", which)
+        alt = _post(spec).log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
+        assert np.array_equal(np.isneginf(alt), np.isneginf(ref)), which
+        assert np.all(np.abs(alt[fin] - ref[fin]) <= 1e-7 + 1e-11 * np.abs(ref[fin])), which
 
 
 def test_gp_not_positive_definite_and_bad_hyperparameters(cuda):

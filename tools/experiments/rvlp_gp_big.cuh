@@ -48,14 +48,6 @@ __host__ __device__ inline GpBigSmem gp_big_smem(const DevProblem& P, const Smem
   return G;
 }
 
-// D(8x8) += A(8x4) B(4x8), fp64 tensor-core MMA.  Fragments (PTX ISA, m8n8k4 .f64): a = A[lane / 4][lane % 4],
-// b = B[lane % 4][lane / 4], {c0, c1} = C[lane / 4][2 (lane % 4) + {0, 1}].
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
-
 // NW warps per CTA (= per sample), MB CTAs per SM.
 template <bool PRED, int NW, int MB>
 __global__ void __launch_bounds__(32 * NW, MB)

@@ -7,13 +7,14 @@ from ravest_b200 import fit, workloads, _lib
 
 peak, _ = _lib.measure_fp64_peak(0, 4096)
 res = []
-CASES = ((120, 10000, False), (120, 10000, True), (200, 4000, False), (200, 4000, True), (220, 4000, True),
-         (256, 4000, True), (384, 2000, True), (512, 2000, True), (768, 1000, True), (1024, 600, True), (2048, 300, True))
-if len(sys.argv) > 1:
-    CASES = tuple(c for c in CASES if c[2] and c[0] in (200, 256, 512, 1024))
+CASES = []
+SEL = os.environ.get("GPT_KERNELS", "default,big,batch").split(",")
+for N, S in ((30, 20000), (57, 20000), (120, 10000), (120, 1000), (120, 100), (200, 4000), (256, 4000), (512, 2000), (1024, 600), (1024, 32), (2048, 300)):
+    for k in SEL:
+        CASES.append((N, S, k))
 for N, S, force in CASES:
-    if force:
-        os.environ["RVLP_GP_KERNEL"] = "big"
+    if force != "default":
+        os.environ["RVLP_GP_KERNEL"] = force
     else:
         os.environ.pop("RVLP_GP_KERNEL", None)
     spec, theta = workloads.make_c5(n_samples=S, n_planets=1, n_epochs=N, seed=505)
@@ -31,7 +32,7 @@ for N, S, force in CASES:
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 3
     flops = N ** 3 / 3.0 + 100.0 * N * (N - 1) / 2      # Cholesky + covariance build (SURVEY 8d weights)
-    r = {"shape": os.environ.get("RVLP_GP_BIG_SHAPE", "82"), "N": N, "S": S, "kernel": "big" if force else "pipe", "ms": round(ms, 3), "us_per_sample": round(1e3 * ms / S, 3),
+    r = {"shape": os.environ.get("RVLP_GP_BIG_SHAPE", "82"), "N": N, "S": S, "kernel": force, "ms": round(ms, 3), "us_per_sample": round(1e3 * ms / S, 3),
          "logprob_per_s": round(S / ms * 1e3), "chol_tflops": round(S * N ** 3 / 3.0 / ms / 1e9, 2),
          "frac_of_fp64_peak": round(S * flops / (ms * 1e-3) / peak, 3)}
     res.append(r)
