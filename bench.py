@@ -259,20 +259,35 @@ def run_reference(args) -> None:
 
 
 # ---------------------------------------------------------------------------------------------- GPU timing
-def time_kernel(torch, fn, steps: int, warmup: int, barrier) -> float:
-    """CUDA-event time (ms) of `steps` calls on the current stream, max over ranks done by the caller."""
+L2_BYTES = 126 << 20
+
+
+def time_kernel(torch, fn, steps: int, warmup: int, barrier, flush=None) -> float:
+    """CUDA-event time (ms) of `steps` calls on the current stream, max over ranks done by the caller.
+    flush: a device buffer larger than L2; when given it is rewritten BETWEEN the timed iterations (each iteration has
+    its own event pair, the flush sits outside them) so that no iteration finds its inputs in L2."""
     for _ in range(warmup):
         fn()
     barrier()
     torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(steps):
+    if flush is None:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        barrier()
+        return a.elapsed_time(b)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.add_(1)                       # read + write 2 x L2 bytes
+        a.record()
         fn()
-    b.record()
+        b.record()
     torch.cuda.synchronize()
     barrier()
-    return a.elapsed_time(b)
+    return float(sum(a.elapsed_time(b) for a, b in ev))
 
 
 def time_host(torch, fn, steps: int, warmup: int, barrier) -> float:
@@ -383,7 +398,8 @@ def other_workloads(torch, fit, barrier, name, peak_flops) -> dict:
                 # (mean model 4.9e4 + covariance build 7.1e5 + Cholesky N^3/3 5.8e5 + solve / log-det 2e4)
                 entry["flops_per_logprob"] = 1.36e6
                 entry["roofline_frac"] = entry["logprob_per_s"] * 1.36e6 / peak_flops
-                entry["kernel"] = "rvlp::gp_logprob_pipe_kernel<6, false>"
+                entry["kernel"] = ("rvlp::gpb_step_kernel<1> x 7 (+ prologue, diag0, finish): level-synchronous batched "
+                                   "Cholesky, DMMA Gram sums (rvlp_gp_batch.cuh)")
                 if hw:
                     entry["hw"] = hw
             n_chk = 2000 if other != "c5" else 300
@@ -478,14 +494,21 @@ def main() -> None:
                 gathered[0] = recv if world > 1 else part
 
         ctx.logprob(th, out=part)                                   # first call autotunes (synchronous), outside any timing
+        # timing rule: inputs larger than L2, or L2 flushed between the timed iterations
+        flush = None
+        if theta.nbytes <= L2_BYTES * 1.5:
+            flush = torch.zeros(2 * L2_BYTES, dtype=torch.uint8, device="cuda")
         sampler = ClockSampler(local) if (rank == 0 and with_clocks) else None
         if sampler:
             sampler.start()
         n0 = ravest_b200.launch_count()
-        ms = time_kernel(torch, step, steps, warmup, barrier)
+        ms = time_kernel(torch, step, steps, warmup, barrier, flush)
         launches = ravest_b200.launch_count() - n0 - warmup
         clocks = sampler.stop() if sampler else None
-        ms_kernel = time_kernel(torch, lambda: ctx.logprob(th, out=part), steps, 1, barrier)
+        ms_kernel = time_kernel(torch, lambda: ctx.logprob(th, out=part), steps, 1, barrier, flush)
+        l2_note = (f"theta is {theta.nbytes / 1e6:.0f} MB per GPU (> 126 MB L2), streamed once per step" if flush is None else
+                   f"theta is {theta.nbytes / 1e6:.0f} MB per GPU: L2 flushed between the timed iterations (a {2 * L2_BYTES >> 20} MB "
+                   f"buffer rewritten outside the per-iteration event pairs)")
 
         # cross-GPU bit check: rank 0 evaluates ALL rows on its own GPU and compares with what the ranks gathered
         bit_identical = None
@@ -506,7 +529,7 @@ def main() -> None:
         return dict(spec=spec, theta=theta, theta_all=theta_all, post=post, units=units, total=total, ms=ms,
                     ms_kernel=ms_kernel, e2e_ms=e2e_ms, e2e_pinned_ms=e2e_pinned_ms, launches=launches, clocks=clocks,
                     bit_identical=bit_identical, same=bool(same), rows_local=hi - lo, steps=steps, warmup=warmup,
-                    part=part)
+                    part=part, l2_note=l2_note)
 
     primary = measure(args.scaling, args.steps, args.warmup, True)
     other_mode = None
@@ -557,9 +580,7 @@ def main() -> None:
                        "samples_per_gpu": m["rows_local"], "epochs": len(spec["time"]),
                        "planets": len(spec["planet_letters"]), "ndim": int(theta.shape[1]),
                        "parallelism": par if world > 1 else "single GPU",
-                       "l2": (f"theta is {theta.nbytes / 1e6:.0f} MB per GPU, streamed once per step"
-                              + (" (> 126 MB L2)" if theta.nbytes > 126e6 else
-                                 "; < 126 MB L2: the kernel is fp64-bound at 0.05 B/unit, L2 residency of theta does not change its time"))},
+                       "l2": m["l2_note"]},
             "logprob_per_s": m["total"] * steps / (m["ms"] * 1e-3),
             "e2e": {"value": m["units"] * steps / (m["e2e_ms"] * 1e-3), "unit": "evals/s",
                     "h2d_bytes_per_step": int(theta.nbytes) * world if args.scaling == "weak" else int(m["theta_all"].nbytes),

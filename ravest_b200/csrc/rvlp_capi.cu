@@ -226,10 +226,13 @@ static int launch_gp_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doub
     if ((rc = grid_for(c->device, (const void*)gpb_diag0_kernel, 0, (n + kGbWarps - 1) / kGbWarps, &grid, kGbThreads))) return rc;
     gpb_diag0_kernel<<<grid, kGbThreads, 0, st>>>(P, n, w);
     g_launches += 2;
+    const int tpw = N >= 300 ? 2 : 1;                            // row blocks per warp of the step kernel (see there)
     for (int J = 0; J + 1 < d.nbr; ++J) {
-      const int64_t tasks = n * (int64_t)(d.nbr - 1 - J);       // one warp per (sample, row block below the diagonal)
-      if ((rc = grid_for(c->device, (const void*)gpb_step_kernel, 0, (tasks + kGbWarps - 1) / kGbWarps, &grid, kGbThreads))) return rc;
-      gpb_step_kernel<<<grid, kGbThreads, 0, st>>>(P, n, w, J);
+      const int64_t tasks = n * (int64_t)((d.nbr - 1 - J + tpw - 1) / tpw);   // one warp per (sample, group of row blocks)
+      const void* kern = tpw == 2 ? (const void*)gpb_step_kernel<2> : (const void*)gpb_step_kernel<1>;
+      if ((rc = grid_for(c->device, kern, 0, (tasks + kGbWarps - 1) / kGbWarps, &grid, kGbThreads))) return rc;
+      if (tpw == 2) gpb_step_kernel<2><<<grid, kGbThreads, 0, st>>>(P, n, w, J);
+      else gpb_step_kernel<1><<<grid, kGbThreads, 0, st>>>(P, n, w, J);
       ++g_launches;
     }
     int64_t gf = (n + 127) / 128;
@@ -246,20 +249,23 @@ static int launch_gp_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doub
   return RVLP_OK;
 }
 
-// Which GP implementation serves a call.  N >= 220: the batched path always (the pipelined kernels do not exist there).
-// N <= 219: the pipelined one-CTA-per-sample kernel for small batches (one launch, ~50 us latency) and for
-// 81..149 epochs; the batched path from 2048 samples on where it measured faster (profiles/r02_gp_kernels_time.log:
-// N = 30: 0.26 vs 0.37 ms per 2e4, N = 57: 0.76 vs 0.81, N = 120: 1.53 vs 1.46 per 1e4, N = 200: 1.90 vs 3.15 per 4e3).
+// Which GP implementation serves a call (profiles/r02q_gp_crossover.log: both paths, N = 16..219, 1024 and 8192 samples).
+// N >= 220 (or no pipelined shape): the batched path always.  N <= 219: the pipelined one-CTA-per-sample kernel for
+// small batches (one launch, ~50 us latency) and wherever its register tiles fit well (33..88 epochs); the batched
+// path from 140 epochs on (1.2x at 144, 2.1x at 176), and for >= 4096 samples also at <= 32 and >= 89 epochs
+// (N = 120: 1.33 vs 1.46 ms per 1e4).  The conditioning path switches at 140 epochs only.
 // RVLP_GP_KERNEL = pipe | batch forces one (tests, experiments).
 enum { GP_PIPE = 0, GP_BATCH = 2 };
-static int gp_choice(const rvlp_ctx* c, int64_t S) {
+static int gp_choice(const rvlp_ctx* c, int64_t S, bool pred) {
   if (c->gp_tile == 0) return GP_BATCH;
   if (const char* e = getenv("RVLP_GP_KERNEL")) {
     if (!strcmp(e, "batch")) return GP_BATCH;
     if (!strcmp(e, "pipe")) return GP_PIPE;
   }
   const int N = c->P.n_epochs;
-  return (S >= 2048 && (N <= 80 || N >= 150)) ? GP_BATCH : GP_PIPE;
+  if (N >= 140 && S >= 512) return GP_BATCH;
+  if (!pred && S >= 4096 && (N <= 32 || N >= 89)) return GP_BATCH;
+  return GP_PIPE;
 }
 
 extern "C" {
@@ -740,7 +746,7 @@ int rvlp_gp_logprob_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
   if (S == 0) return RVLP_OK;
   DeviceGuard guard(c->device);
   cudaStream_t st = (cudaStream_t)stream;
-  const int which = gp_choice(c, S);
+  const int which = gp_choice(c, S, false);
   if (which == GP_BATCH) return launch_gp_batch<false>(c, theta_dev, S, out_dev, nullptr, st);
   int grid = 0, rc;
   const char* grid_cap = getenv("RVLP_GP_GRID");          // tests / experiments: cap the grid (e.g. 148 = one CTA per SM)
@@ -801,7 +807,7 @@ int rvlp_gp_predict_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const
     ~BetaFree() { cudaFreeAsync(p, st); }
   } beta_free{d_beta, st};
   int grid = 0, rc = RVLP_OK;
-  const int which = gp_choice(c, S);
+  const int which = gp_choice(c, S, true);
   if (which == GP_BATCH) {
     if ((rc = launch_gp_batch<true>(c, theta_dev, S, chi2_dev, d_beta, st))) return rc;
   } else {

@@ -30,8 +30,12 @@ constexpr int kGbNB = 16;           // block size
 constexpr int kGbWarps = 4;         // warps per CTA of the step kernel = row blocks of one sample per task group
 constexpr int kGbThreads = 32 * kGbWarps;
 constexpr int kGbLd = 17;           // padded leading dimension of shared-memory tiles
+constexpr int kGbLdT = 16;          // leading dimension of the per-warp L_JJ copy (read as broadcasts)
 #ifndef RVLP_GPB_ABLATE           // timing experiments only (wrong results): 1 no covariance chains, 2 no triangular solve,
 #define RVLP_GPB_ABLATE 0         // 4 no Gram loop, 8 no diagonal-block factorisation
+#endif
+#ifndef RVLP_GPB_TUNE             // 1 fix-up-free covariance path for interior tiles, 4 clamp-only exp (both +1 % at
+#define RVLP_GPB_TUNE 5           // N = 120, profiles/r02s_gpb_tune.log; a transposed L_JJ for the solve lost 3 %)
 #endif
 #ifndef RVLP_GPB_MB
 #define RVLP_GPB_MB 4               // CTAs per SM the step kernel is compiled for (register cap = 65536 / (128 MB))
@@ -92,6 +96,8 @@ struct GpbSample {
 // Entries (i, j) and (i, j + 1) of the augmented, padded matrix, for two rows at once: four independent covariance
 // chains (branch-free) followed by the fix-ups - white-noise diagonal (fit.py:8094-8096), residual row N, identity
 // padding below it.  Only the lower triangle is ever used.
+// INTERIOR (compile time): the tile lies strictly below the diagonal and above row N - no fix-ups, no clamps.
+template <bool INTERIOR>
 __device__ __forceinline__ void gpb_entries4(const GpbSample& sm, int i0, int i1, int j, double (&v)[4]) {
   const int N = sm.N;
   const int ii[2] = {i0, i1};
@@ -99,8 +105,8 @@ __device__ __forceinline__ void gpb_entries4(const GpbSample& sm, int i0, int i1
   int ic[2], jc[2];
 #pragma unroll
   for (int a = 0; a < 2; ++a) {
-    ic[a] = ii[a] < N ? ii[a] : N - 1;
-    jc[a] = j + a < N ? j + a : N - 1;
+    ic[a] = (INTERIOR || ii[a] < N) ? ii[a] : N - 1;
+    jc[a] = (INTERIOR || j + a < N) ? j + a : N - 1;
     tv[a] = sm.t[ic[a]];
     tj[a] = sm.t[jc[a]];
     ci[a] = sm.cph[ic[a]]; si[a] = sm.sph[ic[a]];
@@ -116,8 +122,9 @@ __device__ __forceinline__ void gpb_entries4(const GpbSample& sm, int i0, int i1
     for (int b = 0; b < 2; ++b) {
       const double cd = fma(ci[a], cj[b], si[a] * sj[b]);
       const double q = (tv[a] - tj[b]) * sm.hyp.inv_le;
-      v[a * 2 + b] = (RVLP_GPB_ABLATE & 1) ? cd + q : gp_exp_scaled(fma(g2, cd, fma(-0.5 * q, q, -g2)), sm.hyp.A2);
+      v[a * 2 + b] = (RVLP_GPB_ABLATE & 1) ? cd + q : ((RVLP_GPB_TUNE & 4) ? gp_exp_scaled_neg(fma(g2, cd, fma(-0.5 * q, q, -g2)), sm.hyp.A2) : gp_exp_scaled(fma(g2, cd, fma(-0.5 * q, q, -g2)), sm.hyp.A2));
     }
+  if (INTERIOR) return;
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -282,17 +289,23 @@ __device__ __forceinline__ GpbSample gpb_sample(const DevProblem& P, const GpbWo
 }
 
 // C tile (I, J) minus the accumulated Gram sums, from the DMMA accumulator layout into a shared-memory tile.
-__device__ __forceinline__ void gpb_tile_to_smem(const GpbSample& sm, int I, int J, const double (&acc)[4][2], double* tile,
-                                                 int g, int q) {
+template <bool INTERIOR>
+__device__ __forceinline__ void gpb_tile_to_smem_t(const GpbSample& sm, int I, int J, const double (&acc)[4][2], double* tile,
+                                                   int g, int q) {
 #pragma unroll
   for (int cb = 0; cb < 2; ++cb) {                          // column half: tiles (0, cb) and (1, cb) share the columns
     double v[4];
-    gpb_entries4(sm, I * kGbNB + g, I * kGbNB + 8 + g, J * kGbNB + cb * 8 + 2 * q, v);
+    gpb_entries4<INTERIOR>(sm, I * kGbNB + g, I * kGbNB + 8 + g, J * kGbNB + cb * 8 + 2 * q, v);
     tile[g * kGbLd + cb * 8 + 2 * q] = v[0] - acc[cb][0];
     tile[g * kGbLd + cb * 8 + 2 * q + 1] = v[1] - acc[cb][1];
     tile[(8 + g) * kGbLd + cb * 8 + 2 * q] = v[2] - acc[2 + cb][0];
     tile[(8 + g) * kGbLd + cb * 8 + 2 * q + 1] = v[3] - acc[2 + cb][1];
   }
+}
+__device__ __forceinline__ void gpb_tile_to_smem(const GpbSample& sm, int I, int J, const double (&acc)[4][2], double* tile,
+                                                 int g, int q) {
+  if ((RVLP_GPB_TUNE & 1) && I > J && I * kGbNB + kGbNB - 1 < sm.N) gpb_tile_to_smem_t<true>(sm, I, J, acc, tile, g, q);   // warp-uniform
+  else gpb_tile_to_smem_t<false>(sm, I, J, acc, tile, g, q);
 }
 
 // ------------------------------------------------------------------ diagonal block 0
@@ -319,26 +332,32 @@ gpb_diag0_kernel(DevProblem P, int64_t S, GpbWork w) {
 }
 
 // ------------------------------------------------------------------ block column J
-// One WARP per (sample, row block I > J); warps never synchronise with each other.  Consecutive warps take consecutive
-// row blocks of the same sample, so the shared operands (block row J, L_JJ) hit in L1.
+// One WARP per (sample, group of TPW consecutive row blocks I > J); warps never synchronise with each other.
+// TPW = 2 (two 16 x 16 tiles per warp): the B operand (block row J) is loaded once for both, all 32 lanes work in the
+// triangular solve (one row each) and the per-task fixed costs are halved - faster from ~300 epochs on (N = 1024:
+// 16.7 -> 15.2 ms per 600 samples); TPW = 1 keeps the registers and twice the tasks - faster below (N = 120: 1.34 vs
+// 1.40 ms per 1e4).  Consecutive warps take consecutive groups of the same sample, so the shared operands hit in L1.
+template <int TPW>
 __global__ void __launch_bounds__(kGbThreads, RVLP_GPB_MB)
 gpb_step_kernel(DevProblem P, int64_t S, GpbWork w, int J) {
-  __shared__ double ljj_s[kGbWarps][kGbNB * kGbLd];
+  __shared__ __align__(16) double ljj_s[kGbWarps][kGbNB * kGbLdT];
   __shared__ double invd_s[kGbWarps][kGbNB];
-  __shared__ double tiles[kGbWarps][kGbNB * kGbLd];
+  __shared__ double tiles[kGbWarps][TPW][kGbNB * kGbLd];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
   const GpbDims d = gpb_dims(P.n_epochs);
   const int nI = d.nbr - 1 - J;                                  // row blocks below the diagonal block
-  const int64_t total = S * (int64_t)nI;
+  const int nP = (nI + TPW - 1) / TPW;                           // groups of them
+  const int64_t total = S * (int64_t)nP;
   double* ljj = ljj_s[warp];
   double* invd_j = invd_s[warp];
-  double* tile = tiles[warp];
-  const int rl = lane & (kGbNB - 1);
+  const int rl = lane & (kGbNB - 1), tsel = TPW == 2 ? lane >> 4 : 0;   // solve: row rl of tile tsel
   for (int64_t task = (int64_t)blockIdx.x * kGbWarps + warp; task < total; task += (int64_t)gridDim.x * kGbWarps) {
-    const int64_t s = task / nI;
-    const int I = J + 1 + (int)(task - s * nI);
+    const int64_t s = task / nP;
+    const int I0 = J + 1 + TPW * (int)(task - s * nP);
     if (w.status[s] != 0) continue;
-    const bool next_diag = I == J + 1;
+    const bool two = TPW == 2 && I0 + 1 < d.nbr;                 // the last group of an odd count has one tile
+    const int I1 = two ? I0 + 1 : I0;                            // (the second tile then repeats the first and stores nothing)
+    const bool next_diag = I0 == J + 1;
     // L_JJ and 1 / diag: the loads are issued here and parked in registers; they go to shared memory after the Gram
     // loop, whose operand loads they overlap with
     double2 ljj_r[4];
@@ -349,39 +368,54 @@ gpb_step_kernel(DevProblem P, int64_t S, GpbWork w, int J) {
     }
     const double invd_r = w.invd[(size_t)s * d.np + J * kGbNB + rl];
     const GpbSample sm = gpb_sample(P, w, d, s);
-    // ---- sum_{K<J} L_IK L_JK^T (and L_IK L_IK^T for the next diagonal block) on the tensor cores
-    double acc[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
-    double gram[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
-    const double* arow = gpb_block(w, d, s, I, 0) + g * kGbNB + q;   // blocks (I, 0..J-1) are contiguous
+    // ---- sum_{K<J} L_IK L_JK^T per tile (and L_I0K L_I0K^T for the next diagonal block) on the tensor cores
+    double acc[TPW][4][2] = {};
+    double gram[4][2] = {};
+    const double* arow[TPW];
+    arow[0] = gpb_block(w, d, s, I0, 0) + g * kGbNB + q;          // blocks (I, 0..J-1) are contiguous
+    if (TPW == 2) arow[TPW - 1] = gpb_block(w, d, s, I1, 0) + g * kGbNB + q;
     const double* brow = gpb_block(w, d, s, J, 0) + g * kGbNB + q;
+    const int Jend = (RVLP_GPB_ABLATE & 4) ? 0 : J;
     if (next_diag) {
 #pragma unroll 1
-      for (int K = 0; K < J; ++K) {
+      for (int K = 0; K < Jend; ++K) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          const double a0 = arow[K * 256 + 4 * kk], a1 = arow[K * 256 + 128 + 4 * kk];
-          const double b0 = brow[K * 256 + 4 * kk], b1 = brow[K * 256 + 128 + 4 * kk];
-          dmma884(acc[0][0], acc[0][1], a0, b0);
-          dmma884(acc[1][0], acc[1][1], a0, b1);
-          dmma884(acc[2][0], acc[2][1], a1, b0);
-          dmma884(acc[3][0], acc[3][1], a1, b1);
-          dmma884(gram[0][0], gram[0][1], a0, a0);
-          dmma884(gram[1][0], gram[1][1], a0, a1);
-          dmma884(gram[2][0], gram[2][1], a1, a0);
-          dmma884(gram[3][0], gram[3][1], a1, a1);
+          const int o = K * 256 + 4 * kk;
+          const double b0 = brow[o], b1 = brow[o + 128];
+          double a0[TPW], a1[TPW];
+#pragma unroll
+          for (int t = 0; t < TPW; ++t) { a0[t] = arow[t][o]; a1[t] = arow[t][o + 128]; }
+#pragma unroll
+          for (int t = 0; t < TPW; ++t) {
+            dmma884(acc[t][0][0], acc[t][0][1], a0[t], b0);
+            dmma884(acc[t][1][0], acc[t][1][1], a0[t], b1);
+            dmma884(acc[t][2][0], acc[t][2][1], a1[t], b0);
+            dmma884(acc[t][3][0], acc[t][3][1], a1[t], b1);
+          }
+          dmma884(gram[0][0], gram[0][1], a0[0], a0[0]);
+          dmma884(gram[1][0], gram[1][1], a0[0], a1[0]);
+          dmma884(gram[2][0], gram[2][1], a1[0], a0[0]);
+          dmma884(gram[3][0], gram[3][1], a1[0], a1[0]);
         }
       }
     } else {
 #pragma unroll 1
-      for (int K = 0; K < ((RVLP_GPB_ABLATE & 4) ? 0 : J); ++K) {
+      for (int K = 0; K < Jend; ++K) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          const double a0 = arow[K * 256 + 4 * kk], a1 = arow[K * 256 + 128 + 4 * kk];
-          const double b0 = brow[K * 256 + 4 * kk], b1 = brow[K * 256 + 128 + 4 * kk];
-          dmma884(acc[0][0], acc[0][1], a0, b0);
-          dmma884(acc[1][0], acc[1][1], a0, b1);
-          dmma884(acc[2][0], acc[2][1], a1, b0);
-          dmma884(acc[3][0], acc[3][1], a1, b1);
+          const int o = K * 256 + 4 * kk;
+          const double b0 = brow[o], b1 = brow[o + 128];
+          double a0[TPW], a1[TPW];
+#pragma unroll
+          for (int t = 0; t < TPW; ++t) { a0[t] = arow[t][o]; a1[t] = arow[t][o + 128]; }
+#pragma unroll
+          for (int t = 0; t < TPW; ++t) {
+            dmma884(acc[t][0][0], acc[t][0][1], a0[t], b0);
+            dmma884(acc[t][1][0], acc[t][1][1], a0[t], b1);
+            dmma884(acc[t][2][0], acc[t][2][1], a1[t], b0);
+            dmma884(acc[t][3][0], acc[t][3][1], a1[t], b1);
+          }
         }
       }
     }
@@ -389,28 +423,32 @@ gpb_step_kernel(DevProblem P, int64_t S, GpbWork w, int J) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int idx = e * 32 + lane;
-      ljj[(idx >> 3) * kGbLd + 2 * (idx & 7)] = ljj_r[e].x;
-      ljj[(idx >> 3) * kGbLd + 2 * (idx & 7) + 1] = ljj_r[e].y;
+      *reinterpret_cast<double2*>(ljj + (idx >> 3) * kGbLdT + 2 * (idx & 7)) = ljj_r[e];
     }
     if (lane < kGbNB) invd_j[lane] = invd_r;
-    gpb_tile_to_smem(sm, I, J, acc, tile, g, q);
+    gpb_tile_to_smem(sm, I0, J, acc[0], tiles[warp][0], g, q);
+    if (TPW == 2) gpb_tile_to_smem(sm, I1, J, acc[TPW - 1], tiles[warp][TPW - 1], g, q);
     __syncwarp();
-    // ---- X L_JJ^T = P: one lane per row (lanes 16..31 shadow rows 0..15 and store nothing).  Column-oriented: once
-    // x_k is final, the updates of x_{k+1..15} are independent of each other (a 32-deep dependency chain, not 136).
+    // ---- X L_JJ^T = P: one lane per row (TPW = 1: lanes 16..31 shadow rows 0..15 and store nothing).  Column-oriented:
+    // once x_k is final, the updates of x_{k+1..15} are independent of each other (a 32-deep dependency chain, not 136).
     double x[kGbNB];
+    {
+      const double* trow = tiles[warp][tsel] + rl * kGbLd;
 #pragma unroll
-    for (int c = 0; c < kGbNB; ++c) x[c] = tile[rl * kGbLd + c];
+      for (int c = 0; c < kGbNB; ++c) x[c] = trow[c];
+    }
 #pragma unroll
     for (int k = 0; k < ((RVLP_GPB_ABLATE & 2) ? 1 : kGbNB); ++k) {
       x[k] *= invd_j[k];
 #pragma unroll
-      for (int c = k + 1; c < kGbNB; ++c) x[c] = fma(-x[k], ljj[c * kGbLd + k], x[c]);
+      for (int c = k + 1; c < kGbNB; ++c) x[c] = fma(-x[k], ljj[c * kGbLdT + k], x[c]);
     }
-    if (lane < kGbNB) {
-      double* dst = gpb_block(w, d, s, I, J) + lane * kGbNB;
+    if (TPW == 2 ? (tsel == 0 || two) : lane < kGbNB) {
+      const int It = tsel ? I1 : I0;
+      double* dst = gpb_block(w, d, s, It, J) + rl * kGbNB;
 #pragma unroll
       for (int c = 0; c < kGbNB; c += 2) *reinterpret_cast<double2*>(dst + c) = make_double2(x[c], x[c + 1]);
-      if (I == d.IR && lane == d.rr) {                            // alpha's entries of block column J (all < N)
+      if (It == d.IR && rl == d.rr) {                             // alpha's entries of block column J (all < N)
         double qs = 0.0;
 #pragma unroll
         for (int c = 0; c < kGbNB; ++c) qs = fma(x[c], x[c], qs);
@@ -419,10 +457,11 @@ gpb_step_kernel(DevProblem P, int64_t S, GpbWork w, int J) {
     }
     // ---- the next diagonal block: Gram sum over blocks 0..J (the last one from the tile just solved), factor, publish
     if (next_diag && !(RVLP_GPB_ABLATE & 8)) {
+      double* tile = tiles[warp][0];
       __syncwarp();
-      if (lane < kGbNB) {
+      if (TPW == 2 ? tsel == 0 : lane < kGbNB) {
 #pragma unroll
-        for (int c = 0; c < kGbNB; ++c) tile[lane * kGbLd + c] = x[c];
+        for (int c = 0; c < kGbNB; ++c) tile[rl * kGbLd + c] = x[c];
       }
       __syncwarp();
 #pragma unroll
@@ -434,13 +473,13 @@ gpb_step_kernel(DevProblem P, int64_t S, GpbWork w, int J) {
         dmma884(gram[3][0], gram[3][1], a1, a1);
       }
       __syncwarp();
-      gpb_tile_to_smem(sm, I, I, gram, tile, g, q);
+      gpb_tile_to_smem(sm, I0, I0, gram, tile, g, q);
       __syncwarp();
       double inv_own;
 #pragma unroll
       for (int c = 0; c < kGbNB; ++c) x[c] = tile[rl * kGbLd + c];
       gpb_factor_rows(x, inv_own, lane);
-      gpb_publish_rows(w, d, s, I, x, inv_own, lane);
+      gpb_publish_rows(w, d, s, I0, x, inv_own, lane);
     }
   }
 }

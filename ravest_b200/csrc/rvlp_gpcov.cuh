@@ -128,6 +128,29 @@ RV_HD double gp_exp_scaled(double y, double scale) {
   return ffma(ts, p, ts) * scale;
 }
 
+// The same for y <= 0 (or NaN), the only values the covariance function produces: one clamp instead of the range logic
+// (exp(y) below 2^-1021 is returned as ~3e-308 * scale; NaN propagates).
+RV_HD double gp_exp_scaled_neg(double y, double scale) {
+  y = y < -708.0 ? -708.0 : y;
+  const double t = ffma(y, RVG(0), RINT_MAGIC);    // n = rint(64 y / ln 2)
+  const double nf = t - RINT_MAGIC;
+  double r = ffma(nf, RVG(1), y);
+  r = ffma(nf, RVG(2), r);                         // |r| <= ln2 / 128
+  const int n = lo32(t);
+#if defined(__CUDA_ARCH__)
+  const double tj = __ldg(&kExp2TabDev[n & 63]);
+#else
+  const double tj = kExp2TabHost[n & 63];
+#endif
+  const double two_e = from_hi(((n >> 6) + 1023) << 20);
+  double w = ffma(r, RVG(3), RVG(4));
+  w = ffma(r, w, RVG(5));
+  w = ffma(r, w, RVG(6));
+  const double p = ffma(r * r, w, r);              // exp(r) - 1
+  const double ts = tj * two_e;                    // exact
+  return ffma(ts, p, ts) * scale;
+}
+
 // k(tau) without the white-noise diagonal.
 RV_HD double gp_cov(double tau, const GpHyper& h) {
   const double s = gp_sinpi_frac(fabs(tau) * h.inv_P);
