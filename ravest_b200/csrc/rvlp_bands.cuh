@@ -33,6 +33,7 @@ constexpr int kRowsPerIter = kBandThreads / kColBlock;
 constexpr int kMaxTargets = 2 * RVLP_MAX_PERCENTILES;
 constexpr int kLevels = 8;
 constexpr int kCandCap = 1024;            // candidate doubles per column
+constexpr int kModeFastDone = 1000;       // W.mode value: column already finished by the two-pass path (rvlp_bands_fast.cuh)
 #ifndef RVLP_BAND_UNROLL
 #define RVLP_BAND_UNROLL 8
 #endif
@@ -188,7 +189,7 @@ band_level_kernel(const double* __restrict__ A, int64_t S, int64_t T, int level,
     int m = -2;
     if (tid < ncol) {
       const int g = W.mode[c0 + tid];
-      m = (g >= 0 && g < level) ? -2 : -1;
+      m = (g >= 0 && (g < level || g == kModeFastDone)) ? -2 : -1;   // collected earlier, or finished by rvlp_bands_fast.cuh
     }
     mode_s[tid] = m;
   }
@@ -392,6 +393,7 @@ band_finish_kernel(int64_t T, BandTargets tg, BandWorkspace W, double* __restric
   const int64_t c = (int64_t)blockIdx.x * kBandWarps + warp;
   if (c >= T) return;
   const int mode = W.mode[c];
+  if (mode == kModeFastDone) return;                       // warp-uniform: the column's result is already in `out`
   const int L0 = mode >= 0 ? mode : kLevels;
   uint32_t n = 0;
   if (mode >= 0) {

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "rvlp_bands.cuh"
+#include "rvlp_bands_fast.cuh"
 #include "rvlp_gp.cuh"
 #include "rvlp_gp_batch.cuh"
 #include "rvlp_gp_pipe.cuh"
@@ -843,7 +844,7 @@ int rvlp_gp_predict_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const
 
 int64_t rvlp_percentile_workspace_bytes(int64_t n_cols, int32_t n_q) {
   if (n_cols < 0 || n_q < 1 || n_q > RVLP_MAX_PERCENTILES) return -1;
-  return (int64_t)band_ws_bytes(n_cols, 2 * n_q);
+  return (int64_t)(band_ws_bytes(n_cols, 2 * n_q) + band_fast_ws_bytes(n_cols, 2 * n_q));
 }
 
 int rvlp_percentile_columns(const double* A_dev, int64_t S, int64_t T, const double* q_percent, int32_t n_q,
@@ -866,9 +867,10 @@ int rvlp_percentile_columns(const double* A_dev, int64_t S, int64_t T, const dou
   }
   if (!A_dev || !ws_dev) return fail(RVLP_EINVAL, "null matrix / workspace");
   const int R = 2 * n_q;
-  if (ws_bytes < (int64_t)band_ws_bytes(T, R) || ((uintptr_t)ws_dev & 255))
+  const int64_t ws_need = (int64_t)(band_ws_bytes(T, R) + band_fast_ws_bytes(T, R));
+  if (ws_bytes < ws_need || ((uintptr_t)ws_dev & 255))
     return fail(RVLP_EINVAL, "workspace too small (%lld < %lld bytes) or not 256-byte aligned", (long long)ws_bytes,
-                (long long)band_ws_bytes(T, R));
+                (long long)ws_need);
   // numpy/lib/_function_base_impl.py: q = true_divide(q, 100); method "linear": virtual index = (n - 1) * q
   // (its comment: preferred to _compute_virtual_index(n, q, 1, 1) for rounding); _get_indexes (floor, +1,
   // clamped at the ends); _get_gamma = virtual - previous.
@@ -897,11 +899,45 @@ int rvlp_percentile_columns(const double* A_dev, int64_t S, int64_t T, const dou
     CUDA_TRY(cudaFuncSetAttribute(band_level_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(1, kMaxTargets)));
     CUDA_TRY(cudaFuncSetAttribute(band_level_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(1, kMaxTargets)));
     CUDA_TRY(cudaFuncSetAttribute(band_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinishSmem));
+    CUDA_TRY(cudaFuncSetAttribute(band_fast_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kColBlock * (kFastBins + 1) * 4));
+    CUDA_TRY(cudaFuncSetAttribute(band_fast_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kColBlock * (kFastBins + 1) * 4));
+    CUDA_TRY(cudaFuncSetAttribute(band_fast_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastFinishSmem));
     if (device < 64) attr_done.fetch_or(1ull << device);
   }
   int sms = 0;
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   const int64_t ncb = (T + kColBlock - 1) / kColBlock;
+  // ---- two-pass value-space path (rvlp_bands_fast.cuh): finishes every column whose target bins fit its candidate
+  // buffer; the radix path below skips those (a CTA whose columns are all done returns at once)
+  const char* fast_env = getenv("RVLP_BANDS_FAST");         // tests: "0" forces the radix path for every column
+  if (S >= kFastMinRows && !(fast_env && fast_env[0] == '0')) {
+    const BandFastWs F = band_fast_carve(reinterpret_cast<unsigned char*>(ws_dev) + band_ws_bytes(T, R), T, R);
+    CUDA_TRY(cudaMemsetAsync(F.hist, 0, (size_t)T * kFastBins * 4, st));
+    CUDA_TRY(cudaMemsetAsync(F.ncand, 0, (size_t)T * 4, st));
+    band_fast_sample_kernel<<<(unsigned)T, kBandThreads, 0, st>>>(A_dev, S, T, tg, F);
+    const int smem_pass = kColBlock * (kFastBins + 1) * 4;
+    for (int pass = 0; pass < 2; ++pass) {
+      int per_sm = 0;
+      if (pass == 0) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, band_fast_pass_kernel<false>, kBandThreads, smem_pass));
+      else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, band_fast_pass_kernel<true>, kBandThreads, smem_pass));
+      if (per_sm < 1) return fail(RVLP_EUNSUPPORTED, "band kernel does not fit on an SM");
+      int64_t split = (int64_t)sms * per_sm / ncb;          // one wave of resident CTAs, as the radix levels
+      const int64_t max_split = (S + 1023) / 1024;
+      if (split > max_split) split = max_split;
+      if (split < 1) split = 1;
+      if (split > 65535) split = 65535;
+      const dim3 grid((unsigned)ncb, (unsigned)split);
+      if (pass == 0) {
+        band_fast_pass_kernel<false><<<grid, kBandThreads, smem_pass, st>>>(A_dev, S, T, tg, W, F);
+        band_fast_plan_kernel<<<(unsigned)((T + kBandWarps - 1) / kBandWarps), kBandThreads, 0, st>>>(T, tg, W, F);
+      } else {
+        band_fast_pass_kernel<true><<<grid, kBandThreads, smem_pass, st>>>(A_dev, S, T, tg, W, F);
+      }
+    }
+    band_fast_finish_kernel<<<(unsigned)T, kBandThreads, kFastFinishSmem, st>>>(T, tg, W, F, out_dev);
+    g_launches += 5;
+    CUDA_TRY(cudaGetLastError());
+  }
   for (int level = 0; level <= kLevels; ++level) {
     // Row split: every CTA does the same amount of work, so the grid is sized to ONE wave of resident CTAs
     // (a 1.06-wave grid costs two full rounds); at least 1024 rows per CTA keeps the per-CTA scan / merge small.

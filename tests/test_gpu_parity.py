@@ -898,3 +898,48 @@ def test_two_devices_in_one_process(cuda):
         res.append([x.cpu().numpy() for x in (lp, bands, g, mu)])
     for a, b in zip(*res):
         assert np.array_equal(a.view(np.int64), b.view(np.int64))
+
+
+def test_percentile_two_pass_value_space_path(cuda, monkeypatch):
+    """rvlp_bands_fast.cuh (S >= 8192): sample -> value-space bins -> count pass -> collect pass.  Exact for any data
+    (the bins are a monotone map; the sample only sets the speed): adversarial columns, unsorted / extreme q, and
+    identical bits with the radix path forced (RVLP_BANDS_FAST=0) and with numpy."""
+    from ravest_b200 import _lib
+    rng = np.random.default_rng(23)
+    S, T = 50_000, 19
+    A = rng.normal(-2.0, 3.0, size=(S, T))
+    A[:, 1] = np.where(rng.random(S) < 0.5, rng.normal(-1e6, 1.0, S), rng.normal(1e6, 1.0, S))   # bimodal, far apart
+    A[:, 2] = rng.standard_cauchy(S) * 1e3                                                        # heavy tails
+    A[:, 3] = np.sort(A[:, 3])                                                                    # sorted: sample = exact quantiles
+    A[:, 4] = 7.25; A[123, 4] = -1.0                                                              # constant but one
+    A[:, 5] = np.round(A[:, 5] * 0.5)                                                             # few distinct values
+    A[:, 6] = 0.0                                                                                 # all-zero trend column
+    A[::2, 7] = -0.0; A[1::2, 7] = 0.0                                                            # signed zeros only
+    A[:, 8] = rng.standard_normal(S) * 1e-300                                                     # denormal-ish spread
+    A[:, 9] = np.exp(rng.normal(0, 30, S))                                                        # 26 decades
+    A[5, 10] = np.inf; A[6, 10] = -np.inf
+    A[77, 11] = np.nan
+    A[:, 12] = np.arange(S)[::-1] % 1000                                                          # periodic in the row index
+    A[: S // 2, 13] = 1.0                                                                         # half the column one value
+    for q in ([15.85, 50, 84.15], [84.15, 0, 50, 100, 15.85], [99.999, 0.001], 50.0):
+        ref = np.percentile(A, q, axis=0)
+        got = _lib.percentile_columns(A, q)
+        monkeypatch.setenv("RVLP_BANDS_FAST", "0")
+        radix = _lib.percentile_columns(A, q)
+        monkeypatch.delenv("RVLP_BANDS_FAST")
+        assert np.array_equal(got, radix, equal_nan=True), q
+        ok = ~np.isnan(ref)
+        assert np.array_equal(np.isnan(got), np.isnan(ref)) and np.array_equal(got[ok], ref[ok]), q
+        # (the sign of a zero result is not compared: -0.0 and +0.0 tie in numpy's partition, their order is arbitrary)
+    # many rows: ~700 candidates per bin (radix steps inside the finish kernel's selection, key lists in global scratch)
+    S, T = 700_000, 7
+    A = rng.normal(1.0, 2.0, size=(S, T))
+    A[:, 1] = np.round(A[:, 1], 3)                                                                # ties inside every bin
+    A[:, 2] = rng.standard_cauchy(S)
+    A[:, 3] = np.where(rng.random(S) < 0.3, 5.0, A[:, 3])                                         # 30 % one value
+    A[:, 4] = np.float64(np.float32(A[:, 4]))                                                     # low mantissa bits all zero
+    A[:, 5] = 1.0 + rng.random(S) * 2.0 ** -40                                                    # differ in the last 12 bits only
+    for q in ([15.85, 50, 84.15], [2.5, 97.5, 50.0, 16.0, 84.0, 0.1, 99.9, 100.0]):
+        ref = np.percentile(A, q, axis=0)
+        got = _lib.percentile_columns(A, q)
+        assert np.array_equal(got, ref), q
