@@ -20,7 +20,7 @@ CSRC = os.path.join(_HERE, "csrc")
 # RVLP_LIB lets tools/kernel_sweep.py time alternative builds of the same sources; it is not a fallback
 LIB_PATH = os.environ.get("RVLP_LIB") or os.path.join(CSRC, "libravest_b200.so")
 SOURCES = ["rvlp_capi.cu"]
-HEADERS = ["rvlp_math.cuh", "rvlp_kernels.cuh", "rvlp_gp.cuh", "rvlp_gp_batch.cuh", "rvlp_gpcov.cuh", "rvlp_gp_pipe.cuh", "rvlp_bands.cuh", "rvlp_bands_fast.cuh", os.path.join("..", "..", "include", "ravest_b200.h")]
+HEADERS = ["rvlp_math.cuh", "rvlp_kernels.cuh", "rvlp_gp.cuh", "rvlp_gp_batch.cuh", "rvlp_gp_smem.cuh", "rvlp_gpcov.cuh", "rvlp_gp_pipe.cuh", "rvlp_bands.cuh", "rvlp_bands_fast.cuh", os.path.join("..", "..", "include", "ravest_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -20,6 +20,7 @@
 #include "rvlp_gp.cuh"
 #include "rvlp_gp_batch.cuh"
 #include "rvlp_gp_pipe.cuh"
+#include "rvlp_gp_smem.cuh"
 #include "rvlp_kernels.cuh"
 
 using namespace rvlp;
@@ -250,19 +251,82 @@ static int launch_gp_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doub
   return RVLP_OK;
 }
 
+// Shared-memory tensor-core Cholesky (rvlp_gp_smem.cuh): one 4-warp CTA per sample in flight; the prologue kernel of
+// the batched path supplies residual / phases / hyperparameters / flags through a small per-sample workspace.
+static int launch_gp_smem(rvlp_ctx* c, const double* theta_dev, int64_t S, double* out_dev, cudaStream_t st) {
+  DevProblem P = c->P;
+  P.epochs_global = 1;
+  const int N = P.n_epochs;
+  const GpbDims d = gpb_dims(N);
+    const int smem_f = gps_smem_bytes(N);
+  const int smem_pro = smem_layout(P).total;
+  if (smem_f > c->max_smem || smem_pro > c->max_smem)
+    return fail(RVLP_EUNSUPPORTED, "shared-memory GP kernel: %d epochs need %d B per CTA (> %d)", N, smem_f, c->max_smem);
+  int rc = ensure_pool(c->device);
+  if (rc) return rc;
+  void (*kern)(DevProblem, int64_t, GpbWork, unsigned long long*, double*) = gps_factor_kernel;
+  CUDA_TRY(cudaFuncSetAttribute(gpb_prologue_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+  const size_t per = ((size_t)(3 * d.np + 4 + P.n_inst + 4) * 8 + 8 + 255) & ~(size_t)255;
+  int64_t chunk = (int64_t)(((size_t)2 << 30) / per);
+  if (const char* e = getenv("RVLP_GP_BATCH_MB")) {         // tests: force chunking
+    if (atoi(e) > 0) chunk = (int64_t)(((size_t)atoi(e) << 20) / per);
+  }
+  if (chunk < 1) chunk = 1;
+  if (chunk > S) chunk = S;
+  unsigned char* slab = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&slab, (size_t)chunk * per + 8192, st));
+  struct SlabFree {
+    void* p; cudaStream_t st;
+    ~SlabFree() { cudaFreeAsync(p, st); }
+  } slab_free{slab, st};
+  GpbWork w{};
+  unsigned long long* ticket = nullptr;
+  {
+    unsigned char* o = slab;
+    auto take = [&](size_t bytes) { unsigned char* r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+    ticket = (unsigned long long*)take(8);
+    w.resid = (double*)take((size_t)chunk * d.np * 8);
+    w.cph = (double*)take((size_t)chunk * d.np * 8);
+    w.sph = (double*)take((size_t)chunk * d.np * 8);
+    w.hyp = (double*)take((size_t)chunk * 4 * 8);
+    w.jit2 = (double*)take((size_t)chunk * P.n_inst * 8);
+    w.lp = (double*)take((size_t)chunk * 8);
+    w.lhp = (double*)take((size_t)chunk * 8);
+    w.chi2 = (double*)take((size_t)chunk * 8);
+    w.logdet = (double*)take((size_t)chunk * 8);
+    w.status = (int*)take((size_t)chunk * 4);
+    if ((size_t)(o - slab) > (size_t)chunk * per + 8192) return fail(RVLP_ECUDA, "internal: GP workspace carve overflow");
+  }
+  for (int64_t s0 = 0; s0 < S; s0 += chunk) {
+    const int64_t n = S - s0 < chunk ? S - s0 : chunk;
+    int grid = 0;
+    if ((rc = grid_for(c->device, (const void*)gpb_prologue_kernel<false>, smem_pro, (n + kWarps - 1) / kWarps, &grid))) return rc;
+    CUDA_TRY(cudaMemsetAsync(ticket, 0, 8, st));
+    gpb_prologue_kernel<false><<<grid, kThreads, smem_pro, st>>>(P, theta_dev + s0 * P.ndim, n, w);
+    if ((rc = grid_for(c->device, (const void*)kern, smem_f, n, &grid, kGsThreads))) return rc;
+    kern<<<grid, kGsThreads, smem_f, st>>>(P, n, w, ticket, out_dev + s0);
+    g_launches += 2;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return RVLP_OK;
+}
+
 // Which GP implementation serves a call (profiles/r02q_gp_crossover.log: both paths, N = 16..219, 1024 and 8192 samples).
 // N >= 220 (or no pipelined shape): the batched path always.  N <= 219: the pipelined one-CTA-per-sample kernel for
 // small batches (one launch, ~50 us latency) and wherever its register tiles fit well (33..88 epochs); the batched
 // path from 140 epochs on (1.2x at 144, 2.1x at 176), and for >= 4096 samples also at <= 32 and >= 89 epochs
 // (N = 120: 1.33 vs 1.46 ms per 1e4).  The conditioning path switches at 140 epochs only.
 // RVLP_GP_KERNEL = pipe | batch forces one (tests, experiments).
-enum { GP_PIPE = 0, GP_BATCH = 2 };
+enum { GP_PIPE = 0, GP_SMEM = 1, GP_BATCH = 2 };
 static int gp_choice(const rvlp_ctx* c, int64_t S, bool pred) {
-  if (c->gp_tile == 0) return GP_BATCH;
+  const bool smem_ok = !pred && gps_smem_bytes(c->P.n_epochs) <= c->max_smem;
   if (const char* e = getenv("RVLP_GP_KERNEL")) {
+    if (!strcmp(e, "smem") && smem_ok) return GP_SMEM;
     if (!strcmp(e, "batch")) return GP_BATCH;
-    if (!strcmp(e, "pipe")) return GP_PIPE;
+    if (!strcmp(e, "pipe") && c->gp_tile != 0) return GP_PIPE;
   }
+  if (c->gp_tile == 0) return GP_BATCH;
   const int N = c->P.n_epochs;
   if (N >= 140 && S >= 512) return GP_BATCH;
   if (!pred && S >= 4096 && (N <= 32 || N >= 89)) return GP_BATCH;
@@ -749,6 +813,7 @@ int rvlp_gp_logprob_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
   cudaStream_t st = (cudaStream_t)stream;
   const int which = gp_choice(c, S, false);
   if (which == GP_BATCH) return launch_gp_batch<false>(c, theta_dev, S, out_dev, nullptr, st);
+  if (which == GP_SMEM) return launch_gp_smem(c, theta_dev, S, out_dev, st);
   int grid = 0, rc;
   const char* grid_cap = getenv("RVLP_GP_GRID");          // tests / experiments: cap the grid (e.g. 148 = one CTA per SM)
 #define RVLP_GP_PIPE(TT)                                                                                    \
