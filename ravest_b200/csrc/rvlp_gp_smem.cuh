@@ -73,48 +73,79 @@ __device__ __forceinline__ void gps_cov2(const GpsView& V, int i, int j, int g, 
   }
 }
 
-// ---- workers.  A tile's own 512-byte slot carries it through both phases, so the phases are runtime loops over small
-// GROUPS of G tiles (rows i0, i0 + step, ...) with no register state between them - one copy of the code instead of
-// one per tile count (the per-count unrolled version stalled on instruction fetch: ncu no_instruction 1.3 per issue).
-//
-// ahead, column jn, one column EARLY (while the diagonal warp factors tile (jn - 1, jn - 1)): the part of the Gram sum
-// that is already final, sum_{k < jn - 1} L_ik L_jn,k^T, subtracted from the covariance entries; the partial tile is
-// parked in its slot in accumulator layout (lane l: doubles 2 l, 2 l + 1).
+// ---- workers.  A tile's own 512-byte slot carries it through its three phases, so every phase is a runtime loop over
+// small GROUPS of G tiles (rows i0, i0 + step, ...) with no register state in between - one copy of the code instead of
+// one per tile count (a per-count unrolled version stalled on instruction fetch: ncu no_instruction 1.3 per issue):
+//   cov   (two columns early)  slot = C_ij, generated in accumulator layout (lane l: doubles 2 l, 2 l + 1);
+//   gram  (one column early)   slot -= sum_{k < j - 1} L_ik L_jk^T - everything but the last term, while the diagonal
+//                              warp still factors tile (j - 1, j - 1); four accumulators cut the DMMA dependency chain;
+//   solve (L_jj^-1 published)  last term k = j - 1, X = (C - G) L_jj^-T as two more DMMA against the published inverse,
+//                              slot = X in fragment order.
 template <int G>
-__device__ __forceinline__ void gps_ahead_group(const GpsView& V, int jn, int i0, int step, int lane) {
+__device__ __forceinline__ void gps_cov_group(const GpsView& V, int jc, int i0, int step, int lane) {
   const int g = lane >> 2, q = lane & 3;
-  double acc[G][2];
+  double v[G][2];
+#pragma unroll
+  for (int t = 0; t < G; ++t) gps_cov2(V, i0 + step * t, jc, g, q, v[t][0], v[t][1]);
+#pragma unroll
+  for (int t = 0; t < G; ++t) {
+    const int i = i0 + step * t;
+    V.Ls[(size_t)(i * (i - 1) / 2 + jc) * 32 + lane] = make_double2(v[t][0], v[t][1]);
+  }
+}
+
+template <int G>
+__device__ __forceinline__ void gps_gram_group(const GpsView& V, int jn, int i0, int step, int lane) {
+  double acc[G][4][2];
   double2* ai[G];
 #pragma unroll
   for (int t = 0; t < G; ++t) {
-    acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) acc[t][h][0] = acc[t][h][1] = 0.0;
     const int i = i0 + step * t;
     ai[t] = V.Ls + (size_t)(i * (i - 1) / 2) * 32 + lane;
   }
   const double2* bj = V.Ls + (size_t)(jn * (jn - 1) / 2) * 32 + lane;
-#pragma unroll 2
-  for (int k = 0; k < jn - 1; ++k) {
-    const double2 b = bj[k * 32];
-    double2 a[G];
+  const int nk = jn - 1;
+  int k = 0;
+#pragma unroll 1
+  for (; k + 1 < nk; k += 2) {
+    const double2 b0 = bj[k * 32], b1 = bj[k * 32 + 32];
+    double2 a0[G], a1[G];
 #pragma unroll
-    for (int t = 0; t < G; ++t) a[t] = ai[t][k * 32];
+    for (int t = 0; t < G; ++t) { a0[t] = ai[t][k * 32]; a1[t] = ai[t][k * 32 + 32]; }
 #pragma unroll
-    for (int t = 0; t < G; ++t) dmma884(acc[t][0], acc[t][1], a[t].x, b.x);
-#pragma unroll
-    for (int t = 0; t < G; ++t) dmma884(acc[t][0], acc[t][1], a[t].y, b.y);
+    for (int t = 0; t < G; ++t) {
+      dmma884(acc[t][0][0], acc[t][0][1], a0[t].x, b0.x);
+      dmma884(acc[t][1][0], acc[t][1][1], a0[t].y, b0.y);
+      dmma884(acc[t][2][0], acc[t][2][1], a1[t].x, b1.x);
+      dmma884(acc[t][3][0], acc[t][3][1], a1[t].y, b1.y);
+    }
   }
-  double v[G][2];
+  if (k < nk) {
+    const double2 b0 = bj[k * 32];
 #pragma unroll
-  for (int t = 0; t < G; ++t) gps_cov2(V, i0 + step * t, jn, g, q, v[t][0], v[t][1]);
+    for (int t = 0; t < G; ++t) {
+      const double2 a0 = ai[t][k * 32];
+      dmma884(acc[t][0][0], acc[t][0][1], a0.x, b0.x);
+      dmma884(acc[t][1][0], acc[t][1][1], a0.y, b0.y);
+    }
+  }
 #pragma unroll
-  for (int t = 0; t < G; ++t) ai[t][jn * 32] = make_double2(v[t][0] - acc[t][0], v[t][1] - acc[t][1]);
+  for (int t = 0; t < G; ++t) {
+    double2 p = ai[t][jn * 32];
+    p.x -= (acc[t][0][0] + acc[t][1][0]) + (acc[t][2][0] + acc[t][3][0]);
+    p.y -= (acc[t][0][1] + acc[t][1][1]) + (acc[t][2][1] + acc[t][3][1]);
+    ai[t][jn * 32] = p;
+  }
 }
 
-// The worker that owns tile ROW jn also prepares the diagonal tile for the diagonal warp: C_jn,jn - sum_{k < jn - 1}
-// L_jn,k L_jn,k^T (accumulator layout) and the matching part of the residual row's sum_k L_jn,k alpha_k go to the
-// double-buffered hand-over block V.dtile.
+// The worker that owns tile ROW jn also prepares the diagonal tile's Gram sum for the diagonal warp (its operands are
+// in this worker's hands anyway): sum_{k < jn - 1} L_jn,k L_jn,k^T (accumulator layout) and the matching part of the
+// residual row's sum_k L_jn,k alpha_k go to the double-buffered hand-over block V.dtile.  (The covariance entries of
+// the diagonal tile are the diagonal warp's own job, in its idle time: gps_diag_cov.)
 __device__ __forceinline__ void gps_ahead_diag(const GpsView& V, int jn, int lane) {
-  const int g = lane >> 2, q = lane & 3;
+  const int q = lane & 3;
   double dg[2] = {0.0, 0.0}, eg[2] = {0.0, 0.0}, part = 0.0;
   const double2* bj = V.Ls + (size_t)(jn * (jn - 1) / 2) * 32 + lane;
   const double* al = V.al + q;
@@ -125,7 +156,12 @@ __device__ __forceinline__ void gps_ahead_diag(const GpsView& V, int jn, int lan
     dmma884(eg[0], eg[1], b.y, b.y);
     part = fma(b.x, al[k * 8], fma(b.y, al[k * 8 + 4], part));
   }
-  double d0, d1;
+  double* h = V.dtile + (jn & 1) * 96;
+  *reinterpret_cast<double2*>(h + 2 * lane) = make_double2(dg[0] + eg[0], dg[1] + eg[1]);
+  h[64 + lane] = part;
+}
+__device__ __forceinline__ void gps_diag_cov(const GpsView& V, int jn, int lane, double& d0, double& d1) {
+  const int g = lane >> 2, q = lane & 3;
   gps_cov2(V, jn, jn, g, q, d0, d1);
   const int row = jn * 8 + g, col = jn * 8 + 2 * q;
   if (row < V.N) {                                         // white noise on the diagonal (fit.py:8094-8096)
@@ -133,34 +169,10 @@ __device__ __forceinline__ void gps_ahead_diag(const GpsView& V, int jn, int lan
     d0 += row == col ? dn : 0.0;
     d1 += row == col + 1 ? dn : 0.0;
   }
-  double* h = V.dtile + (jn & 1) * 96;
-  *reinterpret_cast<double2*>(h + 2 * lane) = make_double2(d0 - (dg[0] + eg[0]), d1 - (dg[1] + eg[1]));
-  h[64 + lane] = part;
 }
 
-// solve, column j (L_jj is published): the last term of the Gram sum (k = j - 1, stored by the previous column's
-// solve), X L_jj^T = C - G in accumulator layout (the published L_jj is STRICTLY lower, zeros elsewhere: no per-lane
-// conditions), then the tile goes back to its slot in fragment order: element (row g, column cc) at double
-// 2 (4 g + cc % 4) + cc / 4, two STS.64 per lane.
-struct GpsLjj {
-  double lr0[8], lr1[8], ivd[8], i0s, i1s;                 // rows 2 q and 2 q + 1 of L_jj (strictly lower part), 1 / diag
-};
-__device__ __forceinline__ void gps_load_ljj(const GpsView& V, int lane, GpsLjj& L) {
-  const int q = lane & 3;
-#pragma unroll
-  for (int m = 0; m < 8; m += 2) {
-    const double2 x0 = *reinterpret_cast<const double2*>(V.ljj + (2 * q) * 8 + m);
-    const double2 x1 = *reinterpret_cast<const double2*>(V.ljj + (2 * q + 1) * 8 + m);
-    const double2 iv = *reinterpret_cast<const double2*>(V.invd + m);
-    L.lr0[m] = x0.x; L.lr0[m + 1] = x0.y;
-    L.lr1[m] = x1.x; L.lr1[m + 1] = x1.y;
-    L.ivd[m] = iv.x; L.ivd[m + 1] = iv.y;
-  }
-  L.i0s = V.invd[2 * q];
-  L.i1s = V.invd[2 * q + 1];
-}
 template <int G>
-__device__ __forceinline__ void gps_solve_group(const GpsView& V, const GpsLjj& L, int j, int i0, int step, int lane) {
+__device__ __forceinline__ void gps_solve_group(const GpsView& V, double2 w, int j, int i0, int step, int lane) {
   const int g = lane >> 2, q = lane & 3, quad = lane & ~3;
   double2* slot[G];
   double c[G][2];
@@ -174,49 +186,45 @@ __device__ __forceinline__ void gps_solve_group(const GpsView& V, const GpsLjj& 
   }
   if (j > 0) {
     const double2 b = V.Ls[(size_t)(j * (j - 1) / 2 + j - 1) * 32 + lane];
-    double e[G][2];
+    double e[G][2], f[G][2];
 #pragma unroll
     for (int t = 0; t < G; ++t) {
       const double2 a = slot[t][lane - 32];                // tile (i, j - 1) sits right before (i, j)
-      e[t][0] = e[t][1] = 0.0;
+      e[t][0] = e[t][1] = f[t][0] = f[t][1] = 0.0;
       dmma884(e[t][0], e[t][1], a.x, b.x);
-      dmma884(e[t][0], e[t][1], a.y, b.y);
+      dmma884(f[t][0], f[t][1], a.y, b.y);
     }
 #pragma unroll
     for (int t = 0; t < G; ++t) {
-      c[t][0] -= e[t][0];
-      c[t][1] -= e[t][1];
+      c[t][0] -= e[t][0] + f[t][0];
+      c[t][1] -= e[t][1] + f[t][1];
     }
   }
-#pragma unroll
-  for (int m = 0; m < 7; ++m) {
-#pragma unroll
-    for (int t = 0; t < G; ++t) {
-      const double xm = __shfl_sync(0xffffffffu, (m & 1) ? c[t][1] : c[t][0], quad | (m >> 1)) * L.ivd[m];   // X[g][m]
-      if (m < 6) c[t][0] = fma(-xm, L.lr0[m], c[t][0]);    // (column 2 q <= 6)
-      c[t][1] = fma(-xm, L.lr1[m], c[t][1]);
-    }
-  }
+  // accumulator layout -> A-fragment layout inside the quad: P[g][q] and P[g][4 + q]
+  const int s0 = quad | (q >> 1), s1 = s0 | 2;
   const int e0 = 2 * (4 * g + ((2 * q) & 3)) + ((2 * q) >> 2), e1 = 2 * (4 * g + ((2 * q + 1) & 3)) + ((2 * q + 1) >> 2);
 #pragma unroll
   for (int t = 0; t < G; ++t) {
+    const double u0 = __shfl_sync(0xffffffffu, c[t][0], s0), u1 = __shfl_sync(0xffffffffu, c[t][1], s0);
+    const double v0 = __shfl_sync(0xffffffffu, c[t][0], s1), v1 = __shfl_sync(0xffffffffu, c[t][1], s1);
+    const double ax = (q & 1) ? u1 : u0, ay = (q & 1) ? v1 : v0;
+    double x0 = 0.0, x1 = 0.0, y0 = 0.0, y1 = 0.0;
+    dmma884(x0, x1, ax, w.x);                              // X = P W^T, W = L_jj^-1 in fragment order
+    dmma884(y0, y1, ay, w.y);
     double* tile = reinterpret_cast<double*>(slot[t]);
-    tile[e0] = c[t][0] * L.i0s;
-    tile[e1] = c[t][1] * L.i1s;
+    tile[e0] = x0 + y0;
+    tile[e1] = x1 + y1;
   }
 }
 
-// ---- diagonal warp: 8 x 8 Cholesky of tile (j, j) in accumulator layout, alpha_j as a ninth row; publishes the
-// strictly lower part of L_jj (row-major, zeros elsewhere), 1 / diag, alpha_j, and adds this block's chi^2 / sum ln L_kk.
-// The pivot chain is shuffle -> reciprocal (seed + 3 fp64 operations) -> two multiplies -> shuffle; the reciprocal
-// square roots that scale L are off it.
-__device__ __forceinline__ void gps_factor_diag(const GpsView& V, int j, int lane, double c0, double c1, double part, double* red) {
+// ---- diagonal warp: 8 x 8 Cholesky of tile (j, j) in accumulator layout with the INVERSE of the factor built along
+// (forward substitution on the identity, one step behind the pivots); publishes W = L_jj^-1 in fragment order.  The
+// pivot chain is shuffle -> reciprocal (seed + 3 fp64 operations) -> two multiplies -> shuffle; the reciprocal square
+// roots that scale L and W are off it.  Returns W (accumulator layout) and the product of the pivots.
+__device__ __forceinline__ void gps_factor_diag(const GpsView& V, int lane, double c0, double c1, double& w0, double& w1, double& p8) {
   const int g = lane >> 2, q = lane & 3, quad = lane & ~3;
-  part += __shfl_xor_sync(0xffffffffu, part, 1);
-  part += __shfl_xor_sync(0xffffffffu, part, 2);
-  double z = V.r[j * 8 + g] - part;                        // lanes (g, 0) carry the residual row
-  double inv[8];
-  double p8 = 1.0, chi = 0.0;
+  double z0 = g == 2 * q ? 1.0 : 0.0, z1 = g == 2 * q + 1 ? 1.0 : 0.0;
+  p8 = 1.0;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const double mine = (k & 1) ? c1 : c0;                 // this lane's entry of column pair k / 2
@@ -225,34 +233,22 @@ __device__ __forceinline__ void gps_factor_diag(const GpsView& V, int j, int lan
     const double cgk = __shfl_sync(0xffffffffu, low, quad | (k >> 1));             // C[g][k], g > k
     const double ck0 = __shfl_sync(0xffffffffu, low, (2 * q) * 4 + (k >> 1));      // C[2q][k], 2q > k
     const double ck1 = __shfl_sync(0xffffffffu, low, (2 * q + 1) * 4 + (k >> 1));  // C[2q+1][k], 2q+1 > k
-    const double zk = __shfl_sync(0xffffffffu, z, k * 4);
+    const double zk0 = __shfl_sync(0xffffffffu, z0, k * 4 + q), zk1 = __shfl_sync(0xffffffffu, z1, k * 4 + q);
     const double sg = cgk * rcp64_3(piv);
     c0 = fma(-sg, ck0, c0);
     c1 = fma(-sg, ck1, c1);
-    inv[k] = pivot_rsqrt(piv);
+    const double inv = pivot_rsqrt(piv);
     p8 = piv > 0.0 ? p8 * piv : __longlong_as_double(0x7ff8000000000000ll);        // not positive definite -> NaN (as jax)
-    const double ak = zk * inv[k];                         // alpha[8 j + k]
-    chi = fma(ak, ak, chi);
-    z = fma(-ak * inv[k], cgk, z);                         // L[g][k] = C[g][k] / sqrt(pivot)
-    if (lane == 0) V.al[j * 8 + k] = ak;
+    const double wk0 = zk0 * inv, wk1 = zk1 * inv;         // row k of W
+    const double lgk = cgk * inv;                          // L[g][k], 0 for g <= k
+    z0 = g == k ? wk0 : fma(-lgk, wk0, z0);
+    z1 = g == k ? wk1 : fma(-lgk, wk1, z1);
   }
-  double i0s = inv[0], i1s = inv[1];
-#pragma unroll
-  for (int m = 1; m < 4; ++m) {
-    i0s = q == m ? inv[2 * m] : i0s;
-    i1s = q == m ? inv[2 * m + 1] : i1s;
-  }
-  *reinterpret_cast<double2*>(V.ljj + g * 8 + 2 * q) = make_double2(2 * q < g ? c0 * i0s : 0.0, 2 * q + 1 < g ? c1 * i1s : 0.0);
-  if (lane < 8) {
-    double iv = inv[0];
-#pragma unroll
-    for (int m = 1; m < 8; ++m) iv = lane == m ? inv[m] : iv;
-    V.invd[lane] = iv;
-  }
-  if (lane == 0) {
-    red[0] += chi;
-    red[1] += 0.5 * log(p8);
-  }
+  w0 = z0;
+  w1 = z1;
+  const int e0 = 2 * (4 * g + ((2 * q) & 3)) + ((2 * q) >> 2), e1 = 2 * (4 * g + ((2 * q + 1) & 3)) + ((2 * q + 1) >> 2);
+  V.ljj[e0] = z0;
+  V.ljj[e1] = z1;
 }
 
 // One kernel for every epoch count that fits (the tile count per worker is a runtime loop).
@@ -307,7 +303,6 @@ gps_factor_kernel(DevProblem P, int64_t S, GpbWork w, unsigned long long* __rest
       V.r[i] = in ? w.resid[(size_t)s * np_w + i] : 0.0;
       V.dn[i] = in ? ep_e2[i] + w.jit2[(size_t)s * P.n_inst + ep_inst[i]] : 0.0;
     }
-    if (tid == 0) { red_s[0] = 0.0; red_s[1] = 0.0; }
     V.inv_le = w.hyp[(size_t)s * 4 + 1];
     V.g2 = 0.5 * w.hyp[(size_t)s * 4 + 2];
     V.A2 = w.hyp[(size_t)s * 4 + 3];
@@ -323,30 +318,37 @@ gps_factor_kernel(DevProblem P, int64_t S, GpbWork w, unsigned long long* __rest
     if (warp < kGsWorkers) {
       // ------------------------------------------------ worker: tiles (i, j), i > j, i % 4 == warp
       auto first_row = [&](int j) { return j + 1 + (warp + (kGsWorkers - 1) * (j + 1)) % kGsWorkers; };   // first i > j, i % W == warp
-      auto ahead = [&](int jn) {
-        int i = first_row(jn);
+      auto cov_col = [&](int jc) {
+        int i = first_row(jc);
 #pragma unroll 1
-        for (; i + kGsWorkers < NT; i += 2 * kGsWorkers) gps_ahead_group<2>(V, jn, i, kGsWorkers, lane);
-        if (i < NT) gps_ahead_group<1>(V, jn, i, kGsWorkers, lane);
-        if (jn % kGsWorkers == warp) gps_ahead_diag(V, jn, lane);
+        for (; i + kGsWorkers < NT; i += 2 * kGsWorkers) gps_cov_group<2>(V, jc, i, kGsWorkers, lane);
+        if (i < NT) gps_cov_group<1>(V, jc, i, kGsWorkers, lane);
       };
-      ahead(0);
+      cov_col(0);
+      if (warp == 0) gps_ahead_diag(V, 0, lane);
+      if (NT > 1) cov_col(1);
       gps_bar_sync(2, kGsThreads);                         // tile (0, 0) is handed over
 #pragma unroll 1
       for (int j = 0; j < NT; ++j) {
         GPS_STAMP(0)
-        if (j + 1 < NT) ahead(j + 1);                      // next column's early part, while the diagonal warp factors
+        if (j + 1 < NT) {                                  // next column's early part, while the diagonal warp factors
+          if ((j + 1) % kGsWorkers == warp) gps_ahead_diag(V, j + 1, lane);
+          int i = first_row(j + 1);
+#pragma unroll 1
+          for (; i + kGsWorkers < NT; i += 2 * kGsWorkers) gps_gram_group<2>(V, j + 1, i, kGsWorkers, lane);
+          if (i < NT) gps_gram_group<1>(V, j + 1, i, kGsWorkers, lane);
+        }
         GPS_STAMP(1)
+        if (j + 2 < NT) cov_col(j + 2);
         GPS_STAMP(2)
-        gps_bar_sync(1, kGsThreads);                       // L_jj is published
+        gps_bar_sync(1, kGsThreads);                       // W = L_jj^-1 is published
         GPS_STAMP(3)
         int i = first_row(j);
         if (i < NT) {
-          GpsLjj L;
-          gps_load_ljj(V, lane, L);
+          const double2 wf = *reinterpret_cast<const double2*>(V.ljj + 2 * lane);
 #pragma unroll 1
-          for (; i + kGsWorkers < NT; i += 2 * kGsWorkers) gps_solve_group<2>(V, L, j, i, kGsWorkers, lane);
-          if (i < NT) gps_solve_group<1>(V, L, j, i, kGsWorkers, lane);
+          for (; i + kGsWorkers < NT; i += 2 * kGsWorkers) gps_solve_group<2>(V, wf, j, i, kGsWorkers, lane);
+          if (i < NT) gps_solve_group<1>(V, wf, j, i, kGsWorkers, lane);
         }
         GPS_STAMP(4)
         gps_bar_sync(2, kGsThreads);                       // column j of L is in shared memory
@@ -354,31 +356,53 @@ gps_factor_kernel(DevProblem P, int64_t S, GpbWork w, unsigned long long* __rest
       }
     } else {
       // ------------------------------------------------ diagonal warp
+      const int g = lane >> 2, q = lane & 3;
+      double chi = 0.0, logdet = 0.0;
+      double dc0, dc1;
+      gps_diag_cov(V, 0, lane, dc0, dc1);
       gps_bar_sync(2, kGsThreads);                         // tile (0, 0) is handed over
 #pragma unroll 1
       for (int j = 0; j < NT; ++j) {
         GPS_STAMP(0)
         const double* h = V.dtile + (j & 1) * 96;
-        const double2 c01 = *reinterpret_cast<const double2*>(h + 2 * lane);
+        double2 c01 = *reinterpret_cast<const double2*>(h + 2 * lane);
+        c01.x = dc0 - c01.x;
+        c01.y = dc1 - c01.y;
         double part = h[64 + lane];
-        double e0 = 0.0, e1 = 0.0;
+        double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
         if (j > 0) {                                       // last term, k = j - 1
           const double2 b = V.Ls[(size_t)(j * (j - 1) / 2 + j - 1) * 32 + lane];
           dmma884(e0, e1, b.x, b.x);
-          dmma884(e0, e1, b.y, b.y);
-          const int q = lane & 3;
+          dmma884(f0, f1, b.y, b.y);
           part = fma(b.x, V.al[(j - 1) * 8 + q], fma(b.y, V.al[(j - 1) * 8 + 4 + q], part));
         }
         GPS_STAMP(1)
-        gps_factor_diag(V, j, lane, c01.x - e0, c01.y - e1, part, red_s);
+        double w0, w1, p8;
+        gps_factor_diag(V, lane, c01.x - (e0 + f0), c01.y - (e1 + f1), w0, w1, p8);
         __threadfence_block();
         gps_bar_arrive(1, kGsThreads);
         GPS_STAMP(2)
+        // off the critical path: alpha_j = W (r_j - sum_k L_jk alpha_k), chi^2, sum ln L_kk
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        const double zg = V.r[j * 8 + g] - part;           // entry g of the right-hand side, in every lane of quad g
+        const double za = __shfl_sync(0xffffffffu, zg, (2 * q) * 4), zb = __shfl_sync(0xffffffffu, zg, (2 * q + 1) * 4);
+        double ag = fma(w0, za, w1 * zb);
+        ag += __shfl_xor_sync(0xffffffffu, ag, 1);
+        ag += __shfl_xor_sync(0xffffffffu, ag, 2);          // alpha[8 j + g]
+        if (q == 0) V.al[j * 8 + g] = ag;
+        double a2 = q == 0 ? ag * ag : 0.0;
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        chi += a2;
+        logdet += 0.5 * log(p8);
+        if (j + 1 < NT) gps_diag_cov(V, j + 1, lane, dc0, dc1);
         GPS_STAMP(3)
         GPS_STAMP(4)
         gps_bar_sync(2, kGsThreads);
         GPS_STAMP(5)
       }
+      if (lane == 0) { red_s[0] = chi; red_s[1] = logdet; }
     }
     __syncthreads();
     if (tid == 0) {
