@@ -305,6 +305,9 @@ static int launch_gp_smem(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
     CUDA_TRY(cudaMemsetAsync(ticket, 0, 8, st));
     gpb_prologue_kernel<false><<<grid, kThreads, smem_pro, st>>>(P, theta_dev + s0 * P.ndim, n, w);
     if ((rc = grid_for(c->device, (const void*)kern, smem_f, n, &grid, kGsThreads))) return rc;
+    if (const char* e = getenv("RVLP_GP_GRID")) {           // tests / experiments: cap the grid
+      if (atoi(e) > 0 && atoi(e) < grid) grid = atoi(e);
+    }
     kern<<<grid, kGsThreads, smem_f, st>>>(P, n, w, ticket, out_dev + s0);
     g_launches += 2;
     CUDA_TRY(cudaGetLastError());
@@ -312,12 +315,15 @@ static int launch_gp_smem(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
   return RVLP_OK;
 }
 
-// Which GP implementation serves a call (profiles/r02q_gp_crossover.log: both paths, N = 16..219, 1024 and 8192 samples).
-// N >= 220 (or no pipelined shape): the batched path always.  N <= 219: the pipelined one-CTA-per-sample kernel for
-// small batches (one launch, ~50 us latency) and wherever its register tiles fit well (33..88 epochs); the batched
-// path from 140 epochs on (1.2x at 144, 2.1x at 176), and for >= 4096 samples also at <= 32 and >= 89 epochs
-// (N = 120: 1.33 vs 1.46 ms per 1e4).  The conditioning path switches at 140 epochs only.
-// RVLP_GP_KERNEL = pipe | batch forces one (tests, experiments).
+// Which GP implementation serves a call (profiles/r02aa_gp_sweep3.log: the three log-probability paths over 12..200
+// epochs and 256..16384 samples; profiles/r02q_gp_crossover.log for the conditioning path).
+//   log-probability, 40..168 epochs: the shared-memory tensor-core kernel (rvlp_gp_smem.cuh; 1.2-2.1x the others),
+//     except batches under 512 samples below 80 epochs (the pipelined kernel's single launch wins by ~10 %);
+//   169..232 epochs: one shared-memory CTA per SM is left - the batched path from 2048 samples, shared memory below;
+//   under 40 epochs: the pipelined kernel; the batched path for >= 4096 samples at <= 32 epochs;
+//   beyond the pipelined shapes (N >= 220) and the shared-memory budget: the batched path.
+//   Conditioning (K7): pipelined up to 139 epochs or under 512 samples, batched beyond.
+// RVLP_GP_KERNEL = pipe | smem | batch forces one (tests, experiments).
 enum { GP_PIPE = 0, GP_SMEM = 1, GP_BATCH = 2 };
 static int gp_choice(const rvlp_ctx* c, int64_t S, bool pred) {
   const bool smem_ok = !pred && gps_smem_bytes(c->P.n_epochs) <= c->max_smem;
@@ -326,10 +332,14 @@ static int gp_choice(const rvlp_ctx* c, int64_t S, bool pred) {
     if (!strcmp(e, "batch")) return GP_BATCH;
     if (!strcmp(e, "pipe") && c->gp_tile != 0) return GP_PIPE;
   }
-  if (c->gp_tile == 0) return GP_BATCH;
   const int N = c->P.n_epochs;
+  if (smem_ok && N >= 40) {
+    if (N <= 168) return (S < 512 && N < 80 && c->gp_tile != 0) ? GP_PIPE : GP_SMEM;
+    return S >= 2048 ? GP_BATCH : GP_SMEM;
+  }
+  if (c->gp_tile == 0) return GP_BATCH;
   if (N >= 140 && S >= 512) return GP_BATCH;
-  if (!pred && S >= 4096 && (N <= 32 || N >= 89)) return GP_BATCH;
+  if (!pred && S >= 4096 && N <= 32) return GP_BATCH;
   return GP_PIPE;
 }
 

@@ -633,16 +633,16 @@ def test_gp_against_restatement(cuda):
     assert abs(post.log_probability(x) - got[5]) == 0.0
 
 
-@pytest.mark.parametrize("kernel", ["pipe", "batch"])
+@pytest.mark.parametrize("kernel", ["pipe", "batch", "smem"])
 def test_gp_against_sklearn_fixtures(cuda, monkeypatch, kernel):
-    """(kernel = "batch": the level-synchronous batched DMMA path forced onto the same small problems, RVLP_GP_KERNEL.)
+    """(kernel = "batch" / "smem": the level-synchronous batched DMMA path / the shared-memory tensor-core kernel forced
+    onto the same small problems, RVLP_GP_KERNEL; "smem" serves the log-probability only.)
     Rows a17, a18, f-4 against an implementation the builder did not write: tests/golden/gp_sklearn.json holds
     scikit-learn's log marginal likelihood, conditional mean and y^T C^-1 y for the same kernel
     (tests/golden/make_gp_sklearn.py).  Log-probability to the north_star's 1e-7 absolute (+ 1e-11 relative for the
     conditioning of the solve), mean to 1e-8 of its scale, chi^2 to 1e-9 relative."""
     from ravest_b200 import workloads
-    if kernel != "pipe":
-        monkeypatch.setenv("RVLP_GP_KERNEL", kernel)
+    monkeypatch.setenv("RVLP_GP_KERNEL", kernel)
     g = load_golden("gp_sklearn")
     n = 0
     for c in g["cases"]:
@@ -672,7 +672,8 @@ def test_gp_against_sklearn_fixtures(cuda, monkeypatch, kernel):
 @pytest.mark.parametrize("N", [1, 2, 7, 43, 44, 87, 88, 131, 132, 175, 176, 200, 219, 220, 228])
 def test_gp_every_tile_size_and_the_batched_path(cuda, N, monkeypatch):
     """Register-tiled pipelined Cholesky at each tile size boundary (T = 2/4/6/8/10, N <= 219), the batched DMMA path
-    above that, and the batched path forced onto every N against the same oracle."""
+    above that, and every path (pipe, batch, smem: rvlp_gp_smem.cuh, 8 x 8 tiles, padded last tile row when 8 does not
+    divide N) forced onto every N against the same oracle."""
     from oracle import oracle_c
     from ravest_b200 import workloads
     spec, theta = workloads.make_c5(n_samples=48, n_planets=1, n_epochs=N, seed=600 + N)
@@ -682,7 +683,7 @@ def test_gp_every_tile_size_and_the_batched_path(cuda, N, monkeypatch):
     fin = np.isfinite(ref)
     assert fin.sum() > 30
     assert np.all(np.abs(got[fin] - ref[fin]) <= 1e-7 + 1e-11 * np.abs(ref[fin])), np.abs(got[fin] - ref[fin]).max()
-    for which in ("batch"):                 # the other two implementations against the same oracle
+    for which in ("pipe", "batch", "smem"):  # every implementation forced onto the same problem, against the same oracle
         monkeypatch.setenv("RVLP_GP_KERNEL", which)
         alt = _post(spec).log_probability_batch(cuda.as_tensor(theta, device="cuda")).cpu().numpy()
         assert np.array_equal(np.isneginf(alt), np.isneginf(ref)), which
@@ -718,6 +719,7 @@ def test_gp_pipelined_kernel_is_bit_stable_under_grid_size_and_row_order(cuda, m
     CTAs share the work (each CTA overlaps ITS consecutive samples, so the neighbours differ with the grid), not on
     the row order, not on rejected rows sitting in between (they take the barrier-only path)."""
     from ravest_b200 import workloads
+    monkeypatch.setenv("RVLP_GP_KERNEL", "pipe")
     spec, theta = workloads.make_c5(n_samples=700, n_planets=1, n_epochs=N, seed=900 + N)
     names = workloads.free_names(spec) + list(spec["hyperparams"])
     theta[5::37, names.index("gp_amp")] = -1.0                 # rejected rows between good ones
@@ -735,6 +737,49 @@ def test_gp_pipelined_kernel_is_bit_stable_under_grid_size_and_row_order(cuda, m
     assert np.array_equal(got.view(np.int64), base[perm].view(np.int64))
     one = post.log_probability_batch(th[11:12]).cpu().numpy()
     assert one.view(np.int64)[0] == base.view(np.int64)[11]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [9, 40, 57, 64, 100, 120, 128, 136, 160, 176, 230])
+def test_gp_shared_memory_kernel_is_bit_stable_and_matches_the_oracle(cuda, monkeypatch, N):
+    """rvlp_gp_smem.cuh (K3 at 40..168 epochs): against the C restatement, and a sample's bits depend on its own row
+    only - not on the grid (a ticket decides which CTA takes a sample), the chunking of the batch, the row order, or
+    rejected rows in between.  N covers three / two / one CTA per SM and padded last tile rows."""
+    from oracle import oracle_c
+    from ravest_b200 import workloads
+    monkeypatch.setenv("RVLP_GP_KERNEL", "smem")
+    S = 700 if N <= 136 else 160
+    spec, theta = workloads.make_c5(n_samples=S, n_planets=1 + (N % 2), n_epochs=N, seed=4100 + N)
+    names = workloads.free_names(spec) + list(spec["hyperparams"])
+    theta[5::37, names.index("gp_amp")] = -1.0                 # rejected rows between good ones
+    theta[9, names.index("K_b")] = -2.0                        # invalid planet: -inf through the mean model
+    post = _post(spec)
+    th = cuda.as_tensor(theta, device="cuda")
+    base = post.log_probability_batch(th).cpu().numpy()
+    ref = oracle_c.OracleProblem(spec).logprob(theta, nthreads=8)
+    assert np.array_equal(np.isneginf(base), np.isneginf(ref)) and np.isneginf(base[5::37]).all() and np.isneginf(base[9])
+    fin = np.isfinite(ref)
+    assert fin.sum() > 0.9 * S
+    err = np.abs(base[fin] - ref[fin])
+    assert np.all(err <= 1e-7 + 1e-11 * np.abs(ref[fin])), (N, err.max())
+    print(f"[measured] GP smem N = {N}: max |dlogp| vs restatement = {err.max():.3e} (|logp| up to {np.abs(ref[fin]).max():.3e})")
+    for cap in ("1", "7", "148"):
+        monkeypatch.setenv("RVLP_GP_GRID", cap)
+        got = post.log_probability_batch(th).cpu().numpy()
+        assert np.array_equal(got.view(np.int64), base.view(np.int64)), cap
+    monkeypatch.delenv("RVLP_GP_GRID")
+    monkeypatch.setenv("RVLP_GP_BATCH_MB", "1")                # a few hundred samples per chunk
+    got = post.log_probability_batch(th).cpu().numpy()
+    monkeypatch.delenv("RVLP_GP_BATCH_MB")
+    assert np.array_equal(got.view(np.int64), base.view(np.int64))
+    perm = np.random.default_rng(3).permutation(len(theta))
+    got = post.log_probability_batch(cuda.as_tensor(theta[perm], device="cuda")).cpu().numpy()
+    assert np.array_equal(got.view(np.int64), base[perm].view(np.int64))
+    one = post.log_probability_batch(th[11:12]).cpu().numpy()
+    assert one.view(np.int64)[0] == base.view(np.int64)[11]
+    for rep in range(5):                                       # a shared-memory race would show up run to run
+        again = post.log_probability_batch(th).cpu().numpy()
+        assert np.array_equal(again.view(np.int64), base.view(np.int64)), rep
 
 
 @pytest.mark.gpu
@@ -772,6 +817,7 @@ def test_gp_pipelined_kernels_are_run_to_run_deterministic(cuda, monkeypatch):
     """A shared-memory race in the named-barrier pipeline (compute-sanitizer is not available on the pool) would show
     up as run-to-run or grid-to-grid bit differences: ten launches each of K3 and K7 at two grid sizes, bit for bit."""
     from ravest_b200 import workloads
+    monkeypatch.setenv("RVLP_GP_KERNEL", "pipe")
     for N in (120, 57):
         spec, theta = workloads.make_c5(n_samples=1500, n_planets=1, n_epochs=N, seed=77 + N)
         names = workloads.free_names(spec) + list(spec["hyperparams"])
