@@ -398,8 +398,8 @@ def other_workloads(torch, fit, barrier, name, peak_flops) -> dict:
                 # (mean model 4.9e4 + covariance build 7.1e5 + Cholesky N^3/3 5.8e5 + solve / log-det 2e4)
                 entry["flops_per_logprob"] = 1.36e6
                 entry["roofline_frac"] = entry["logprob_per_s"] * 1.36e6 / peak_flops
-                entry["kernel"] = ("rvlp::gpb_step_kernel<1> x 7 (+ prologue, diag0, finish): level-synchronous batched "
-                                   "Cholesky, DMMA Gram sums (rvlp_gp_batch.cuh)")
+                entry["kernel"] = ("rvlp::gps_factor_kernel (+ gpb_prologue_kernel): one 4-warp CTA per sample, factor in "
+                                   "shared memory as 8x8 fragment-order tiles, DMMA Gram sums and solves (rvlp_gp_smem.cuh)")
                 if hw:
                     entry["hw"] = hw
             n_chk = 2000 if other != "c5" else 300
