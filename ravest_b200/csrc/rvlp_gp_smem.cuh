@@ -1,5 +1,5 @@
-// rvlp_gp_smem.cuh — K3 for up to ~136 epochs: one 4-warp CTA per sample in flight, the factor in SHARED MEMORY as
-// 8 x 8 tiles in tensor-core fragment order, every Gram sum on the fp64 tensor cores.
+// rvlp_gp_smem.cuh — K3 for 40..168 epochs (config 5): one 4-warp CTA per sample in flight, the factor in SHARED MEMORY
+// as 8 x 8 tiles in tensor-core fragment order, the whole O(N^3) part on the fp64 tensor cores.
 //
 // GPLogPosterior.log_probability (/root/reference/src/ravest/fit.py:7836-7901, 8062-8105; kernel gp.py:145-156):
 //   C = K(t, t) + diag(sigma^2 + jit^2) = L L^T,  alpha = L^-1 r,  ll = -1/2 alpha.alpha - sum ln L_ii - N/2 ln 2 pi.
@@ -7,24 +7,26 @@
 // Why another kernel.  rvlp_gp_pipe.cuh keeps the triangle in REGISTERS (6 x 6 tiles, DFMA updates): two samples per
 // SM, a barrier-bound dependency chain, 25 % of the fp64 peak at N = 120.  rvlp_gp_batch.cuh keeps it in HBM and pays
 // ~N^3 / 12 bytes of traffic per sample.  Here the factor (54 KB at N = 120: the strictly lower 8 x 8 tiles) stays in
-// shared memory, THREE samples per SM, and the O(N^3) part is `mma.sync.m8n8k4.f64` (SASS DMMA.884): one warp
-// instruction per 256 FMAs keeps an SM sub-partition's fp64 pipe busy for 16 cycles, so the few warps that fit are
-// enough to fill it.  Left-looking by block column j (NT = ceil(N / 8) of them), tile rows dealt round-robin to the
-// four warps starting at the owner of row j:
-//   A. every warp: G_ij = sum_{k<j} L_ik L_jk^T for its tiles (i, j), i >= j - both operands are tiles of L in
-//      "A-fragment order" (lane l holds L[l / 4][l % 4] and L[l / 4][4 + l % 4]; L^T as the B operand has the SAME
-//      lane map), one conflict-free LDS.128 per tile and k; then C_ij - G_ij with the covariance generated on the fly
-//      in accumulator layout (phase-factored periodic term, 19 fp64 instructions per element; C is never stored);
-//   B. the owner of row j does the diagonal tile FIRST: 8 x 8 Cholesky in accumulator layout (quad shuffles; the
-//      reciprocal of the pivot is off the shuffle chain), the residual's entries alpha_j = L_jj^-1 (r_j - sum_k L_jk
-//      alpha_k) ride along as a ninth row; it publishes L_jj, `bar.arrive`s and goes on with its other tiles;
-//   C. the others `bar.sync` on that barrier once their Gram sums are done, solve X L_jj^T = C - G in accumulator
-//      layout and store the tile in fragment order (two STS.64 per lane, no shuffles);
-//   one __syncthreads per block column.
-// Per sample: 1120 DMMA at N = 120 instead of 23.7 k DFMA warp instructions, 15 + 15 barriers instead of ~60.
+// shared memory, THREE samples per SM, and the O(N^3) part is `mma.sync.m8n8k4.f64` (SASS DMMA.8x8x4): one warp
+// instruction per 256 FMAs keeps an SM sub-partition's fp64 pipe busy for 16 cycles (latency 26: tools/dmma_lat.cu), so
+// the few warps that fit are enough to feed it.  Left-looking by block column j (NT = ceil(N / 8) of them):
+//   * a tile of L in "A-fragment order" (lane l holds L[l / 4][l % 4] and L[l / 4][4 + l % 4]) serves as the A operand
+//     AND - L^T as the B operand has the same lane map - as the B operand: one conflict-free LDS.128 per tile and k;
+//   * warps 0..2 are WORKERS (tile rows dealt mod 3).  A tile's own 512-byte slot carries it through three phases that
+//     run ahead of the factorisation front: cov (column j + 2: C_ij generated in accumulator layout, phase-factored
+//     periodic term, 19 fp64 instructions per element), gram (column j + 1: slot -= sum_{k < j} L_ik L_j+1,k^T - all
+//     but the last term), solve (column j: last term, X = (C - G) L_jj^-T as two more DMMA against the published
+//     INVERSE of the diagonal tile, slot = X in fragment order: two STS.64 per lane, no shuffles);
+//   * warp 3 is the DIAGONAL WARP, alone on its SM sub-partition: 8 x 8 Cholesky of tile (j, j) in accumulator layout
+//     (quad shuffles; pivot reciprocal = MUFU seed + 3 fp64 operations on the chain), its inverse built along by forward
+//     substitution on the identity; it publishes W = L_jj^-1 and `bar.arrive`s; then, off the critical path,
+//     alpha_j = W (r_j - sum_k L_jk alpha_k), chi^2, sum ln L_kk and the covariance entries of tile (j + 1, j + 1) (its
+//     Gram sum comes from the worker that owns row j + 1, through a double-buffered hand-over block);
+//   * two named barriers per block column: "W is published" (arrive / sync), "column j is stored".
+// Per sample at N = 120: 1328 DMMA instead of 23.7 k DFMA warp instructions; 0.79 ms per 1e4 samples (1.44 pipelined).
 // The mean model / priors / reject flags come from gpb_prologue_kernel (one warp per sample, rvlp_gp_batch.cuh).
-// Deterministic: fixed summation order per tile, integer ticket only decides WHICH CTA takes a sample - out[s] depends
-// on (theta[s], epochs) only.
+// Deterministic: fixed summation order per tile; the ticket only decides WHICH CTA takes a sample - out[s] depends on
+// (theta[s], epochs) only.  Phase stamps for tuning: -DRVLP_GPS_TRACE + tools/gp_smem_trace.py.
 #pragma once
 #include "rvlp_gp_batch.cuh"
 
