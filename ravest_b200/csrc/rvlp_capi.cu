@@ -13,6 +13,8 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <condition_variable>
+#include <memory>
 #include <vector>
 
 #include "rvlp_bands.cuh"
@@ -637,28 +639,91 @@ int rvlp_info_criteria_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, in
 }
 
 // Pageable -> pinned staging copy.  One thread moves ~8 GB/s, which made the NumPy-in path copy-bound (33 ms against a
-// 24 ms kernel at config 3): large chunks are split over up to four threads.
-static void staged_copy(double* dst, const double* src, size_t nbytes) {
-  const size_t kMinPerThread = (size_t)4 << 20;   // 1 MB per thread was slower below ~10 MB payloads (thread start-up)
-  unsigned hw = std::thread::hardware_concurrency();
-  size_t nt = nbytes / kMinPerThread;
-  if (nt > 4) nt = 4;
-  if (hw > 0 && nt > hw) nt = hw;
-  if (nt < 2) { memcpy(dst, src, nbytes); return; }
-  const size_t per = ((nbytes / nt) + 63) & ~(size_t)63;
-  std::thread th[3];
-  size_t started = 0;
-  for (size_t i = 1; i < nt; ++i) {
-    const size_t b = i * per, e = (i + 1 == nt) ? nbytes : (i + 1) * per;
-    try {
-      th[started] = std::thread([=] { memcpy((char*)dst + b, (const char*)src + b, e - b); });
-      ++started;
-    } catch (...) {                                   // no thread to be had: copy this slice here
-      memcpy((char*)dst + b, (const char*)src + b, e - b);
+// 24 ms kernel at config 3).  A small persistent pool (created on first use, up to 12 threads, never more than three
+// quarters of the host's hardware threads) splits a block into 1 MB slices; the caller copies slices too.
+class StagePool {
+ public:
+  static StagePool& get() {
+    static StagePool* p = new StagePool();   // leaked on purpose: worker threads must not be joined from a static destructor
+    return *p;
+  }
+  void copy(char* dst, const char* src, size_t nbytes) {
+    if (n_workers_ == 0 || nbytes < 4 * kSlice) { memcpy(dst, src, nbytes); return; }
+    auto job = std::make_shared<Job>();      // a late-waking worker keeps ITS job object: it can never touch the next one
+    job->dst = dst; job->src = src; job->nbytes = nbytes;
+    job->nslices = (nbytes + kSlice - 1) / kSlice;
+    job->pending.store((long long)job->nslices);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      job_ = job;
+      ++generation_;
+    }
+    cv_.notify_all();
+    run_slices(*job);
+    std::unique_lock<std::mutex> lk(job->mu);
+    job->done_cv.wait(lk, [&] { return job->pending.load() == 0; });
+  }
+
+ private:
+  static constexpr size_t kSlice = (size_t)1 << 20;
+  struct Job {
+    char* dst = nullptr;
+    const char* src = nullptr;
+    size_t nbytes = 0, nslices = 0;
+    std::atomic<size_t> next{0};
+    std::atomic<long long> pending{0};
+    std::mutex mu;
+    std::condition_variable done_cv;
+  };
+  StagePool() {
+    // profiles/r02ac_host_stage.log (config 3, 232 MB pageable, 16 hardware threads): 2 / 4 / 8 / 12 copying threads ->
+    // 31 / 25 / 23.5 / 22.7-23.3 ms per call against 21.4 ms device-resident
+    unsigned hw = std::thread::hardware_concurrency();
+    unsigned n = hw * 3 / 4 > 12 ? 12 : hw * 3 / 4;
+    if (const char* e = getenv("RVLP_STAGE_THREADS")) n = (unsigned)atoi(e);
+    for (unsigned i = 1; i < n; ++i) {
+      try {
+        std::thread([this] { worker(); }).detach();
+        ++n_workers_;
+      } catch (...) {
+        break;
+      }
     }
   }
-  memcpy(dst, src, per < nbytes ? per : nbytes);
-  for (size_t i = 0; i < started; ++i) th[i].join();
+  static void run_slices(Job& j) {
+    for (;;) {
+      const size_t i = j.next.fetch_add(1);
+      if (i >= j.nslices) break;
+      const size_t b = i * kSlice, e = b + kSlice < j.nbytes ? b + kSlice : j.nbytes;
+      memcpy(j.dst + b, j.src + b, e - b);
+      if (j.pending.fetch_sub(1) == 1) {
+        std::lock_guard<std::mutex> lk(j.mu);
+        j.done_cv.notify_all();
+      }
+    }
+  }
+  void worker() {
+    unsigned long long seen = 0;
+    for (;;) {
+      std::shared_ptr<Job> job;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return generation_ != seen; });
+        seen = generation_;
+        job = job_;
+      }
+      run_slices(*job);
+    }
+  }
+  unsigned n_workers_ = 0;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  unsigned long long generation_ = 0;
+  std::shared_ptr<Job> job_;
+};
+constexpr size_t kStageBlock = (size_t)32 << 20;   // sub-block of a pageable chunk (multiple of 8 bytes)
+static void staged_copy(double* dst, const double* src, size_t nbytes) {
+  StagePool::get().copy(reinterpret_cast<char*>(dst), reinterpret_cast<const char*>(src), nbytes);
 }
 
 int rvlp_logprob_batch_host(rvlp_ctx* c, const double* theta_host, int64_t S, double* out_host) {
@@ -723,8 +788,21 @@ int rvlp_logprob_batch_host(rvlp_ctx* c, const double* theta_host, int64_t S, do
     const int64_t n = bounds[ci] - s0;
     const size_t off = (size_t)s0 * (size_t)c->P.ndim;
     const size_t nbytes = sizeof(double) * (size_t)n * (size_t)c->P.ndim;
-    if (!in_pinned) staged_copy(c->h_theta + off, theta_host + off, nbytes);
-    if (cudaMemcpyAsync(c->d_theta + off, src + off, nbytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+    // A pageable chunk is staged and sent in sub-blocks: the H2D of block b overlaps the staging memcpy of block b + 1,
+    // so a chunk's copy costs ~bytes / (staging rate) instead of bytes / staging + bytes / PCIe - which is what kept
+    // the 1/4 and 1/2 chunks' copies longer than the kernels they were meant to hide behind (e2e 24.6 vs 21.4 ms).
+    size_t sub = in_pinned ? nbytes : kStageBlock;
+    if (const char* e = getenv("RVLP_HOST_STAGE_MB")) {       // experiments
+      if (atoi(e) > 0 && !in_pinned) sub = (size_t)atoi(e) << 20;
+    }
+    bool copy_ok = true;
+    for (size_t b0 = 0; b0 < nbytes && copy_ok; b0 += sub) {
+      const size_t nb = nbytes - b0 < sub ? nbytes - b0 : sub;
+      const size_t o = off + b0 / sizeof(double);
+      if (!in_pinned) staged_copy(c->h_theta + o, theta_host + o, nb);
+      copy_ok = cudaMemcpyAsync(c->d_theta + o, src + o, nb, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    }
+    if (!copy_ok) {
       rc = fail(RVLP_ECUDA, "H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
       break;
     }

@@ -361,8 +361,17 @@ class GPLogLikelihood(_DeviceBacked):
                           free_hyperparams_names=self.gp_kernel.get_expected_hyperparams())
 
     def __call__(self, params: Dict[str, float], hyperparams: Dict[str, float]) -> float:
-        names = self.param_names + self.gp_kernel.get_expected_hyperparams()
+        # fit.py:8062-8105 validates nothing: it squares the jitter (fit.py:8094-8096) and builds the kernel as given
+        # (gp.py:145-156: A^2, tau^2 / lambda_e^2, 1 / (2 lambda_p^2), sin^2(pi tau / P) - even in every
+        # hyperparameter).  The device entry applies GPLogPosterior's rejections (jit < 0, hyperparameter <= 0:
+        # fit.py:7857-7886), so the signs are dropped here: a negative jitter / hyperparameter gives the same finite
+        # value as in the reference instead of -inf.  (Zero / non-finite hyperparameters stay -inf; the reference
+        # returns NaN or raises inside tinygp there.)
+        hyper_names = self.gp_kernel.get_expected_hyperparams()
+        names = self.param_names + hyper_names
         both = dict(params) | dict(hyperparams)
+        for n in hyper_names + [f"jit_{i}" for i in self.unique_instruments]:
+            both[n] = abs(float(both[n]))
         row = np.array([[float(both[n]) for n in names]])
         return float(self.ctx.logprob_host(row)[0])
 

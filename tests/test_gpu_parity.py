@@ -706,6 +706,34 @@ def test_gp_not_positive_definite_and_bad_hyperparameters(cuda):
     assert np.isfinite(got).sum() >= 8
 
 
+def test_gp_loglikelihood_callable_does_not_validate(cuda):
+    """GPLogLikelihood.__call__ (fit.py:8062-8105) squares the jitter and builds the kernel as given - the rejections
+    live in GPLogPosterior.log_probability.  Negative jitter / hyperparameters: same finite value."""
+    from oracle import oracle_py
+    from ravest_b200 import fit, workloads
+    from ravest_b200.gp import GPKernel
+    from ravest_b200.param import Parameterisation
+    spec, theta = workloads.make_c5(n_samples=4, n_planets=1, n_epochs=37, seed=9)
+    names = workloads.free_names(spec) + list(spec["hyperparams"])
+    pr = oracle_py.Problem(spec)
+    gll = fit.GPLogLikelihood(spec["time"], spec["vel"], spec["velerr"], spec["t0"], spec["instrument"],
+                              list(np.unique(spec["instrument"])), list(spec["planet_letters"]),
+                              Parameterisation(spec["parameterisation"]), GPKernel("Quasiperiodic"))
+    row = dict(zip(names, map(float, theta[1])))
+    allp = {k: v[0] for k, v in spec["params"].items()} | {k: row[k] for k in row if not k.startswith("gp_")}
+    hyp = {k: row[k] for k in row if k.startswith("gp_")}
+    base = gll(allp, hyp)
+    ref = pr.gp_log_likelihood(allp, hyp)
+    assert np.isfinite(base) and abs(base - ref) <= 1e-7 + 1e-11 * abs(ref)
+    neg = dict(allp)
+    for k in neg:
+        if k.startswith("jit_"):
+            neg[k] = -abs(neg[k])
+    nh = {k: -v for k, v in hyp.items()}
+    assert gll(neg, nh) == base
+    assert abs(pr.gp_log_likelihood(neg, nh) - ref) <= 1e-9 * abs(ref)
+
+
 def test_fp64_peak_probe(cuda):
     from ravest_b200 import _lib
     flops, ms = _lib.measure_fp64_peak(0, 2048)
