@@ -19,6 +19,8 @@
 // column) use the three bins <a, ==a, >a and need no candidates when the targets fall on the constant.
 // HBM: 2 x S x T x 8 bytes + 1 % for the sample; integer counting only, so the bits do not depend on the grid.
 #pragma once
+#include <type_traits>
+
 #include "rvlp_bands.cuh"
 
 namespace rvlp {
@@ -64,15 +66,19 @@ __host__ __device__ inline BandFastWs band_fast_carve(void* base, int64_t T, int
   return F;
 }
 
-// the monotone value -> bin map (see the header); scale == 0: constant sample
+// the monotone value -> bin map (see the header); scale == 0: constant sample.
+// (x - a) * scale -> floor -> integer clamps: five instructions, no double compares.  cvt.rmi.s32.f64 saturates
+// (-inf -> INT_MIN -> bin 0, +inf -> INT_MAX -> bin 1023) and sends NaN to 0 -> bin 1 (the column is flagged NaN anyway).
+__device__ __forceinline__ int fast_bin_lin(double x, double a, double scale) {
+  const int i = __double2int_rd((x - a) * scale);
+  return max(min(i, kFastBins - 2) + 1, 0);
+}
+__device__ __forceinline__ int fast_bin_const(double x, double a) {   // in key order, so that -0 / +0 / NaN sort as in the radix path
+  const uint64_t kx = key_of(x), ka = key_of(a);
+  return kx < ka ? 0 : (kx == ka ? 1 : kFastBins - 1);
+}
 __device__ __forceinline__ int fast_bin(double x, double a, double scale) {
-  if (scale == 0.0) {                                      // in key order, so that -0 / +0 / NaN sort as in the radix path
-    const uint64_t kx = key_of(x), ka = key_of(a);
-    return kx < ka ? 0 : (kx == ka ? 1 : kFastBins - 1);
-  }
-  const double idx = (x - a) * scale;                      // NaN compares false everywhere: lands in bin 1, the column
-  if (x < a) return 0;                                     // is flagged and returns NaN anyway
-  return idx >= (double)(kFastBins - 2) ? kFastBins - 1 : 1 + (int)idx;
+  return scale == 0.0 ? fast_bin_const(x, a) : fast_bin_lin(x, a, scale);
 }
 
 // Exact selection by the whole CTA: the key of 0-based rank `rk` among list[0, nb) (shared or global memory).  Lists
@@ -251,19 +257,12 @@ band_fast_pass_kernel(const double* __restrict__ A, int64_t S, int64_t T, BandTa
       }
     }
     if (!COLLECT || nt > 0) {
-      int run_bin = -1;
-      uint32_t run_len = 0;
-      auto visit = [&](double x) {
-        const int bin = fast_bin(x, a, scale);
+      // one element; CONST (a constant sample: three bins in key order) is a per-column property, hoisted out of the loop
+      auto visit = [&](double x, auto is_const) {
+        const int bin = decltype(is_const)::value ? fast_bin_const(x, a) : fast_bin_lin(x, a, scale);
         if (!COLLECT) {
           saw_nan |= x != x;
-          if (bin == run_bin) {
-            ++run_len;
-          } else {
-            if (run_len) atomicAdd(hc + run_bin, run_len);
-            run_bin = bin;
-            run_len = 1;
-          }
+          atomicAdd(hc + bin, 1u);                         // (neighbouring samples rarely share a value-space bin: no run lengths)
         } else {
           if (bin >= tlo && bin <= thi && ((mk[bin >> 5] >> (bin & 31)) & 1u)) {
             // staged in shared memory (a global atomic's round trip per candidate stalled the whole warp); the few
@@ -274,30 +273,37 @@ band_fast_pass_kernel(const double* __restrict__ A, int64_t S, int64_t T, BandTa
           }
         }
       };
-      constexpr int U = 8;
-      const int64_t step = (int64_t)kRowsPerIter * U;
-      const int64_t first = r_begin + rl;
-      const int64_t n_full = first + (U - 1) * kRowsPerIter < r_end ? (r_end - first - (U - 1) * kRowsPerIter + step - 1) / step : 0;
-      const double* ptr = col + first * T;
-      const int64_t dstep = step * T, drow = (int64_t)kRowsPerIter * T;
-      double cur[U], nxt[U];
-      if (n_full > 0) {
+      // software pipeline without register moves: two register sets, each loaded while the other is classified
+      auto stream = [&](auto is_const) {
+        constexpr int U = 8;
+        const int64_t drow = (int64_t)kRowsPerIter * T;
+        const double* ptr = col + (r_begin + rl) * T;
+        int64_t left = r_end > r_begin + rl ? (r_end - (r_begin + rl) + kRowsPerIter - 1) / kRowsPerIter : 0;   // this thread's rows
+        double ra[U], rb[U];
+        if (left >= U) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) cur[u] = __ldcs(ptr + u * drow);
-        for (int64_t it = 1; it < n_full; ++it) {
-          ptr += dstep;
+          for (int u = 0; u < U; ++u) ra[u] = __ldcs(ptr + u * drow);
+          ptr += U * drow;
+          left -= U;
+          while (left >= 2 * U) {
 #pragma unroll
-          for (int u = 0; u < U; ++u) nxt[u] = __ldcs(ptr + u * drow);
+            for (int u = 0; u < U; ++u) rb[u] = __ldcs(ptr + u * drow);
 #pragma unroll
-          for (int u = 0; u < U; ++u) visit(cur[u]);
+            for (int u = 0; u < U; ++u) visit(ra[u], is_const);
 #pragma unroll
-          for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+            for (int u = 0; u < U; ++u) ra[u] = __ldcs(ptr + (U + u) * drow);
+#pragma unroll
+            for (int u = 0; u < U; ++u) visit(rb[u], is_const);
+            ptr += 2 * U * drow;
+            left -= 2 * U;
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) visit(ra[u], is_const);
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) visit(cur[u]);
-      }
-      for (int64_t r = first + n_full * step; r < r_end; r += kRowsPerIter) visit(__ldcs(col + r * T));   // tail
-      if (!COLLECT && run_len) atomicAdd(hc + run_bin, run_len);
+        for (; left > 0; --left, ptr += drow) visit(__ldcs(ptr), is_const);   // tail
+      };
+      if (scale == 0.0) stream(std::true_type{});
+      else stream(std::false_type{});
     }
   }
   if (COLLECT) {
