@@ -26,7 +26,11 @@
 namespace rvlp {
 
 constexpr int kFastBins = 1024;
-constexpr int kFastSample = 1024;         // sample rows per column (power of two: bitonic sort)
+#ifndef RVLP_BANDF_SAMPLE
+#define RVLP_BANDF_SAMPLE 256
+#endif
+constexpr int kFastSample = RVLP_BANDF_SAMPLE;   // sample rows per column: 256 -> the bracket is the sample's ~4 % / ~96 % points for
+                                                 // [15.85, 50, 84.15]: 30 % wider bins than with 1024 rows, a quarter of the gather
 constexpr int kFastCap = 4096;            // candidate doubles per column
 constexpr int kFastQuad = 128;            // a key list up to this size is ranked by counting, longer ones by radix steps first
 constexpr int kFastKeysSmem = 1024;       // finish: columns with more candidates keep their key lists in global scratch
@@ -89,14 +93,19 @@ struct BandSelState {
   unsigned long long mn, mx, res;
   uint32_t qn, digit, newrank, bincount;
 };
+// `rk2` (optional, CTA-uniform): a second rank answered by the same counting pass when the list is short - the two
+// ranks of a percentile pair sit in one bin almost always; *res2 is written only then (returns true through `got2`).
 __device__ __forceinline__ uint64_t band_cta_select(const uint64_t* list, uint32_t nb, uint32_t rk, uint64_t* q_s,
-                                                    uint32_t* hist_s, BandSelState* st) {
+                                                    uint32_t* hist_s, BandSelState* st, uint32_t rk2 = 0xffffffffu,
+                                                    uint64_t* res2 = nullptr, bool* got2 = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31;
   uint64_t lo = 0, hi = ~0ull;
   uint32_t live = nb;
+  if (got2) *got2 = false;
   for (;;) {
     __syncthreads();                                       // the previous round's / call's reads of *st are done
     if (live <= (uint32_t)kFastQuad) {
+      const bool pair = res2 != nullptr && live == nb;     // no radix step has narrowed the list: both ranks are in it
       if (tid == 0) st->qn = 0;
       __syncthreads();
       for (uint32_t i = tid; i < nb; i += kBandThreads) {
@@ -113,8 +122,10 @@ __device__ __forceinline__ uint64_t band_cta_select(const uint64_t* list, uint32
           eq += kj == ki ? 1u : 0u;
         }
         if (less <= rk && rk < less + eq) st->res = ki;    // ties write the same key
+        if (pair && less <= rk2 && rk2 < less + eq) st->mx = ki;
       }
       __syncthreads();
+      if (pair) { *res2 = st->mx; *got2 = true; }
       return st->res;
     }
     if (tid == 0) { st->mn = ~0ull; st->mx = 0ull; }
@@ -162,34 +173,48 @@ __device__ __forceinline__ uint64_t band_cta_select(const uint64_t* list, uint32
 }
 
 
-// ---- 0. sample + bracket: one CTA per column gathers the sample and SELECTS its two bracket order statistics (a full
-// sort of the 1024 keys cost 53 us per 1000 columns; two selections cost a few radix steps).  The four columns of a
-// 32-byte sector are fetched by four CTAs and meet in L2.
+// Ascending bitonic sort of n = 2^m keys in shared memory by the whole CTA (one __syncthreads per stage).  A few hundred
+// keys: ~40 stages of n / 2 compare-exchanges - a quarter of the instructions of ranking every key by counting.
+__device__ __forceinline__ void band_cta_sort(uint64_t* k, int n) {
+  const int tid = threadIdx.x;
+  __syncthreads();
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int p = tid; p < n / 2; p += kBandThreads) {
+        const int lo = 2 * p - (p & (stride - 1));         // partner pairs (lo, lo + stride)
+        const bool up = (lo & size) == 0;
+        const uint64_t x = k[lo], y = k[lo + stride];
+        if ((x > y) == up) { k[lo] = y; k[lo + stride] = x; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---- 0. sample + bracket: one CTA per column gathers the sample, sorts it (256 keys: 36 stages) and reads its two
+// bracket order statistics.  The four columns of a 32-byte sector are fetched by four CTAs and meet in L2.
 __global__ void __launch_bounds__(kBandThreads)
 band_fast_sample_kernel(const double* __restrict__ A, int64_t S, int64_t T, BandTargets tg, BandFastWs F) {
+  static_assert((kFastSample & (kFastSample - 1)) == 0, "bitonic sort: power of two");
   __shared__ uint64_t k[kFastSample];
-  __shared__ uint64_t q_s[kFastQuad];
-  __shared__ uint32_t hist_s[256];
-  __shared__ BandSelState st;
   const int tid = threadIdx.x;
   const int64_t c = blockIdx.x;
   for (int i = tid; i < kFastSample; i += kBandThreads) {
     const int64_t row = ((int64_t)i * S) / kFastSample;    // i < 2^10, S < 2^31
     k[i] = key_of(A[row * T + c]);
   }
-  const int R = 2 * tg.n_q;
-  uint32_t kmin = 0xffffffffu, kmax = 0;
-  for (int r = 0; r < R; ++r) { kmin = min(kmin, tg.k[r]); kmax = max(kmax, tg.k[r]); }
-  const double m = (double)kFastSample;
-  const double plo = (double)kmin / (double)S, phi = (double)(kmax + 1) / (double)S;
-  int ra = (int)floor(plo * m - 5.0 * sqrt(m * plo * (1.0 - plo)) - 4.0);
-  int rb = (int)ceil(phi * m + 5.0 * sqrt(m * phi * (1.0 - phi)) + 4.0);
-  ra = ra < 0 ? 0 : ra;
-  rb = rb > kFastSample - 1 ? kFastSample - 1 : rb;
-  __syncthreads();
-  const double a = value_of(band_cta_select(k, kFastSample, (uint32_t)ra, q_s, hist_s, &st));
-  const double b = value_of(band_cta_select(k, kFastSample, (uint32_t)rb, q_s, hist_s, &st));
+  band_cta_sort(k, kFastSample);
   if (tid == 0) {
+    const int R = 2 * tg.n_q;
+    uint32_t kmin = 0xffffffffu, kmax = 0;
+    for (int r = 0; r < R; ++r) { kmin = min(kmin, tg.k[r]); kmax = max(kmax, tg.k[r]); }
+    const double m = (double)kFastSample;
+    const double plo = (double)kmin / (double)S, phi = (double)(kmax + 1) / (double)S;
+    int ra = (int)floor(plo * m - 5.0 * sqrt(m * plo * (1.0 - plo)) - 4.0);
+    int rb = (int)ceil(phi * m + 5.0 * sqrt(m * phi * (1.0 - phi)) + 4.0);
+    ra = ra < 0 ? 0 : ra;
+    rb = rb > kFastSample - 1 ? kFastSample - 1 : rb;
+    const double a = value_of(k[ra]), b = value_of(k[rb]);
     double scale = 0.0;
     if (b > a) {
       scale = (double)(kFastBins - 2) / (b - a);
@@ -450,14 +475,42 @@ band_fast_finish_kernel(int64_t T, BandTargets tg, BandWorkspace W, BandFastWs F
     keys[doff_s[q] + atomicAdd(&dpos_s[q], 1u)] = key_of(x);
   }
   __syncthreads();
+  if (n <= (uint32_t)kFastKeysSmem) {
+    // the usual case: a few hundred candidates.  The bins are monotone in the key, so ONE sort of all candidates puts
+    // the lists one after the other in slot order of their bins: pad to a power of two with the largest key, sort,
+    // index.  (doff_s was laid out in the order the target bins were met; the sorted order is by bin.)
+    uint32_t np2 = 32;
+    while (np2 < n) np2 <<= 1;
+    for (uint32_t i = n + tid; i < np2; i += kBandThreads) key_s[i] = ~0ull;
+    band_cta_sort(key_s, (int)np2);
+    if (tid < R) {
+      const int q = tslot_s[tid];
+      if (q < 0) {
+        v_s[tid] = a;
+      } else {
+        uint32_t below = 0;                                // candidates in target bins below this one
+        for (int p = 0; p < nd; ++p) below += dbin_s[p] < dbin_s[q] ? dcnt_s[p] : 0u;
+        v_s[tid] = value_of(key_s[below + F.trank[(size_t)c * R + tid]]);
+      }
+    }
+  } else
   for (int r = 0; r < R; ++r) {
     const int q = tslot_s[r];                              // CTA-uniform
     if (q < 0) {
       if (tid == 0) v_s[r] = a;
       continue;
     }
-    const uint64_t k = band_cta_select(keys + doff_s[q], dcnt_s[q], F.trank[(size_t)c * R + r], q_s, hist_s, &st);
+    // the partner rank of the pair (k, k + 1) is answered by the same pass when it sits in the same list
+    const bool same = (r & 1) == 0 && tslot_s[r + 1] == q;
+    uint64_t k2 = 0;
+    bool got2 = false;
+    const uint64_t k = band_cta_select(keys + doff_s[q], dcnt_s[q], F.trank[(size_t)c * R + r], q_s, hist_s, &st,
+                                       same ? F.trank[(size_t)c * R + r + 1] : 0xffffffffu, same ? &k2 : nullptr, &got2);
     if (tid == 0) v_s[r] = value_of(k);
+    if (got2) {
+      if (tid == 0) v_s[r + 1] = value_of(k2);
+      ++r;
+    }
   }
   __syncthreads();
   if (tid < tg.n_q) {
