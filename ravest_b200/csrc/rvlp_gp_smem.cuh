@@ -38,13 +38,25 @@ namespace rvlp {
 constexpr int kGsWorkers = RVLP_GPS_WORKERS;        // worker warps: worker w owns the tile rows i with i % kGsWorkers == w
 constexpr int kGsThreads = 32 * (kGsWorkers + 1);   // + the diagonal warp (with 3 workers: an SM sub-partition of its own)
 #ifndef RVLP_GPS_MB
-#define RVLP_GPS_MB 3
+#define RVLP_GPS_MB 4
 #endif
 
 __host__ __device__ inline int gps_tile_rows(int N) { return (N + 7) / 8; }
+// Tile slots.  Tile (i, k), i > k, is written first by `cov` during column k - 2 and read last during column i (as the
+// pivot row's B operand), so along the sub-diagonal d = i - k the tiles k, k + d + 3, k + 2 (d + 3), ... never live at the
+// same time and share a slot: sub-diagonal d needs min(d + 3, NT - d) slots instead of NT - d.  75 slots instead of 105
+// at N = 120 (38 KB): FOUR samples per SM instead of three.  slot(i, k) = base[d] + k mod min(d + 3, NT - d), through a
+// small table in shared memory (gps_fill_slot_table).
+__host__ __device__ inline int gps_diag_slots(int nt, int d) { return d + 3 < nt - d ? d + 3 : nt - d; }
+__host__ __device__ inline int gps_slot_count(int nt) {
+  int n = 0;
+  for (int d = 1; d < nt; ++d) n += gps_diag_slots(nt, d);
+  return n;
+}
+__host__ __device__ inline int gps_tab_bytes(int nt) { return (nt * nt * 2 + 15) & ~15; }
 __host__ __device__ inline int gps_smem_bytes(int N) {
   const int nt = gps_tile_rows(N), np = nt * 8;
-  return nt * (nt - 1) / 2 * 512 + (64 + 8) * 8 + 2 * (64 + 32) * 8 + 6 * np * 8 + 64;
+  return gps_slot_count(nt) * 512 + gps_tab_bytes(nt) + (64 + 8) * 8 + 2 * (64 + 32) * 8 + 6 * np * 8 + 64;
 }
 
 __device__ __forceinline__ void gps_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -53,10 +65,15 @@ __device__ __forceinline__ void gps_bar_arrive(int id, int n) { asm volatile("ba
 // Per-sample shared-memory views and constants of the block-column steps.
 struct GpsView {
   double2* Ls;
+  const unsigned short* tab;                               // [NT][NT] slot of tile (i, k)
   double *ljj, *invd, *dtile, *t, *cph, *sph, *dn, *r, *al;
   double inv_le, g2, A2;
   int N, NT;
 };
+
+__device__ __forceinline__ double2* gps_tile(const GpsView& V, int i, int k) {
+  return V.Ls + (size_t)V.tab[i * V.NT + k] * 32;
+}
 
 // Covariance entries (rows 8 i + g, columns 8 j + 2 q + {0, 1}) in accumulator layout, without the white-noise term.
 // gp.py:145-156 with sin^2(pi tau / P) = (1 - cos(b_i - b_j)) / 2 (rvlp_gp_batch.cuh: gpb_entries4).
@@ -92,53 +109,55 @@ __device__ __forceinline__ void gps_cov_group(const GpsView& V, int jc, int i0, 
 #pragma unroll
   for (int t = 0; t < G; ++t) {
     const int i = i0 + step * t;
-    V.Ls[(size_t)(i * (i - 1) / 2 + jc) * 32 + lane] = make_double2(v[t][0], v[t][1]);
+    gps_tile(V, i, jc)[lane] = make_double2(v[t][0], v[t][1]);
   }
 }
 
 template <int G>
 __device__ __forceinline__ void gps_gram_group(const GpsView& V, int jn, int i0, int step, int lane) {
-  double acc[G][4][2];
-  double2* ai[G];
+  double acc[G][2][2];                                     // two accumulators per tile: DMMA latency 26, issue 16 cycles
+  const unsigned short* ti[G];
 #pragma unroll
   for (int t = 0; t < G; ++t) {
 #pragma unroll
-    for (int h = 0; h < 4; ++h) acc[t][h][0] = acc[t][h][1] = 0.0;
-    const int i = i0 + step * t;
-    ai[t] = V.Ls + (size_t)(i * (i - 1) / 2) * 32 + lane;
+    for (int h = 0; h < 2; ++h) acc[t][h][0] = acc[t][h][1] = 0.0;
+    ti[t] = V.tab + (i0 + step * t) * V.NT;
   }
-  const double2* bj = V.Ls + (size_t)(jn * (jn - 1) / 2) * 32 + lane;
+  const unsigned short* tj = V.tab + jn * V.NT;
+  const double2* L = V.Ls + lane;
   const int nk = jn - 1;
   int k = 0;
 #pragma unroll 1
   for (; k + 1 < nk; k += 2) {
-    const double2 b0 = bj[k * 32], b1 = bj[k * 32 + 32];
+    const double2 b0 = L[tj[k] * 32], b1 = L[tj[k + 1] * 32];
     double2 a0[G], a1[G];
 #pragma unroll
-    for (int t = 0; t < G; ++t) { a0[t] = ai[t][k * 32]; a1[t] = ai[t][k * 32 + 32]; }
+    for (int t = 0; t < G; ++t) { a0[t] = L[ti[t][k] * 32]; a1[t] = L[ti[t][k + 1] * 32]; }
 #pragma unroll
-    for (int t = 0; t < G; ++t) {
-      dmma884(acc[t][0][0], acc[t][0][1], a0[t].x, b0.x);
-      dmma884(acc[t][1][0], acc[t][1][1], a0[t].y, b0.y);
-      dmma884(acc[t][2][0], acc[t][2][1], a1[t].x, b1.x);
-      dmma884(acc[t][3][0], acc[t][3][1], a1[t].y, b1.y);
-    }
+    for (int t = 0; t < G; ++t) dmma884(acc[t][0][0], acc[t][0][1], a0[t].x, b0.x);
+#pragma unroll
+    for (int t = 0; t < G; ++t) dmma884(acc[t][1][0], acc[t][1][1], a0[t].y, b0.y);
+#pragma unroll
+    for (int t = 0; t < G; ++t) dmma884(acc[t][0][0], acc[t][0][1], a1[t].x, b1.x);
+#pragma unroll
+    for (int t = 0; t < G; ++t) dmma884(acc[t][1][0], acc[t][1][1], a1[t].y, b1.y);
   }
   if (k < nk) {
-    const double2 b0 = bj[k * 32];
+    const double2 b0 = L[tj[k] * 32];
 #pragma unroll
     for (int t = 0; t < G; ++t) {
-      const double2 a0 = ai[t][k * 32];
+      const double2 a0 = L[ti[t][k] * 32];
       dmma884(acc[t][0][0], acc[t][0][1], a0.x, b0.x);
       dmma884(acc[t][1][0], acc[t][1][1], a0.y, b0.y);
     }
   }
 #pragma unroll
   for (int t = 0; t < G; ++t) {
-    double2 p = ai[t][jn * 32];
-    p.x -= (acc[t][0][0] + acc[t][1][0]) + (acc[t][2][0] + acc[t][3][0]);
-    p.y -= (acc[t][0][1] + acc[t][1][1]) + (acc[t][2][1] + acc[t][3][1]);
-    ai[t][jn * 32] = p;
+    double2* slot = V.Ls + ti[t][jn] * 32 + lane;
+    double2 p = *slot;
+    p.x -= acc[t][0][0] + acc[t][1][0];
+    p.y -= acc[t][0][1] + acc[t][1][1];
+    *slot = p;
   }
 }
 
@@ -149,11 +168,11 @@ __device__ __forceinline__ void gps_gram_group(const GpsView& V, int jn, int i0,
 __device__ __forceinline__ void gps_ahead_diag(const GpsView& V, int jn, int lane) {
   const int q = lane & 3;
   double dg[2] = {0.0, 0.0}, eg[2] = {0.0, 0.0}, part = 0.0;
-  const double2* bj = V.Ls + (size_t)(jn * (jn - 1) / 2) * 32 + lane;
+  const unsigned short* tj = V.tab + jn * V.NT;
   const double* al = V.al + q;
 #pragma unroll 2
   for (int k = 0; k < jn - 1; ++k) {
-    const double2 b = bj[k * 32];
+    const double2 b = V.Ls[tj[k] * 32 + lane];
     dmma884(dg[0], dg[1], b.x, b.x);
     dmma884(eg[0], eg[1], b.y, b.y);
     part = fma(b.x, al[k * 8], fma(b.y, al[k * 8 + 4], part));
@@ -181,17 +200,17 @@ __device__ __forceinline__ void gps_solve_group(const GpsView& V, double2 w, int
 #pragma unroll
   for (int t = 0; t < G; ++t) {
     const int i = i0 + step * t;
-    slot[t] = V.Ls + (size_t)(i * (i - 1) / 2 + j) * 32;
+    slot[t] = gps_tile(V, i, j);
     const double2 p = slot[t][lane];
     c[t][0] = p.x;
     c[t][1] = p.y;
   }
   if (j > 0) {
-    const double2 b = V.Ls[(size_t)(j * (j - 1) / 2 + j - 1) * 32 + lane];
+    const double2 b = gps_tile(V, j, j - 1)[lane];
     double e[G][2], f[G][2];
 #pragma unroll
     for (int t = 0; t < G; ++t) {
-      const double2 a = slot[t][lane - 32];                // tile (i, j - 1) sits right before (i, j)
+      const double2 a = gps_tile(V, i0 + step * t, j - 1)[lane];
       e[t][0] = e[t][1] = f[t][0] = f[t][1] = 0.0;
       dmma884(e[t][0], e[t][1], a.x, b.x);
       dmma884(f[t][0], f[t][1], a.y, b.y);
@@ -260,8 +279,10 @@ gps_factor_kernel(DevProblem P, int64_t S, GpbWork w, unsigned long long* __rest
   const int N = P.n_epochs, NT = gps_tile_rows(N), NP = NT * 8;
   GpsView V;
   V.N = N; V.NT = NT;
-  V.Ls = reinterpret_cast<double2*>(smem);                                 // [NT (NT - 1) / 2][32] tile (i, k) at i (i - 1) / 2 + k
-  V.ljj = reinterpret_cast<double*>(smem + (size_t)NT * (NT - 1) / 2 * 512);   // [8][8] row-major
+  V.Ls = reinterpret_cast<double2*>(smem);                                 // [gps_slot_count(NT)][32] tile (i, k) at slot tab[i][k]
+  unsigned short* tab_w = reinterpret_cast<unsigned short*>(smem + (size_t)gps_slot_count(NT) * 512);
+  V.tab = tab_w;
+  V.ljj = reinterpret_cast<double*>(smem + (size_t)gps_slot_count(NT) * 512 + gps_tab_bytes(NT));   // W = L_jj^-1, fragment order
   V.invd = V.ljj + 64;                                                     // [8]
   V.dtile = V.invd + 8;                                                    // [2][64 + 32] diagonal-tile hand-over
   V.t = V.dtile + 2 * 96;                                                  // [NP] each
@@ -278,6 +299,16 @@ gps_factor_kernel(DevProblem P, int64_t S, GpbWork w, unsigned long long* __rest
   const double* ep_e2 = P.epochs + 2 * (size_t)P.n_pad;
   const int* ep_inst = reinterpret_cast<const int*>(P.epochs + 3 * (size_t)P.n_pad);
   for (int i = tid; i < NP; i += kGsThreads) V.t[i] = ep_t[i < N ? i : N - 1];
+  for (int idx = tid; idx < NT * NT; idx += kGsThreads) {                  // the slot table (see gps_diag_slots)
+    const int i = idx / NT, k = idx - i * NT;
+    int slot = 0;
+    if (i > k) {
+      const int d = i - k;
+      for (int e = 1; e < d; ++e) slot += gps_diag_slots(NT, e);
+      slot += k % gps_diag_slots(NT, d);
+    }
+    tab_w[idx] = (unsigned short)slot;
+  }
 
   for (;;) {
     __syncthreads();                                       // the previous sample is done with shared memory
@@ -373,7 +404,7 @@ gps_factor_kernel(DevProblem P, int64_t S, GpbWork w, unsigned long long* __rest
         double part = h[64 + lane];
         double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
         if (j > 0) {                                       // last term, k = j - 1
-          const double2 b = V.Ls[(size_t)(j * (j - 1) / 2 + j - 1) * 32 + lane];
+          const double2 b = gps_tile(V, j, j - 1)[lane];
           dmma884(e0, e1, b.x, b.x);
           dmma884(f0, f1, b.y, b.y);
           part = fma(b.x, V.al[(j - 1) * 8 + q], fma(b.y, V.al[(j - 1) * 8 + 4 + q], part));
