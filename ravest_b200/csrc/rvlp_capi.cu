@@ -319,11 +319,12 @@ static int launch_gp_smem(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
 
 // Which GP implementation serves a call (profiles/r02aa_gp_sweep3.log: the three log-probability paths over 12..200
 // epochs and 256..16384 samples; profiles/r02q_gp_crossover.log for the conditioning path).
-//   log-probability, 40..168 epochs: the shared-memory tensor-core kernel (rvlp_gp_smem.cuh; 1.2-2.1x the others),
-//     except batches under 512 samples below 80 epochs (the pipelined kernel's single launch wins by ~10 %);
-//   169..232 epochs: one shared-memory CTA per SM is left - the batched path from 2048 samples, shared memory below;
+//   log-probability, 40..208 epochs: the shared-memory tensor-core kernel (rvlp_gp_smem.cuh; 1.3-2.6x the others -
+//     four samples per SM to 128 epochs, three to 160, two to 208; profiles/r02ag_gp_sweep4.log), except batches under
+//     512 samples below 80 epochs (the pipelined kernel's single launch wins by ~10 %);
 //   under 40 epochs: the pipelined kernel; the batched path for >= 4096 samples at <= 32 epochs;
-//   beyond the pipelined shapes (N >= 220) and the shared-memory budget: the batched path.
+//   beyond (one shared-memory CTA per SM from 209 epochs, no pipelined shape from 220): the batched path from 512
+//     samples, the pipelined kernel below while it has a shape.
 //   Conditioning (K7): pipelined up to 139 epochs or under 512 samples, batched beyond.
 // RVLP_GP_KERNEL = pipe | smem | batch forces one (tests, experiments).
 enum { GP_PIPE = 0, GP_SMEM = 1, GP_BATCH = 2 };
@@ -335,10 +336,7 @@ static int gp_choice(const rvlp_ctx* c, int64_t S, bool pred) {
     if (!strcmp(e, "pipe") && c->gp_tile != 0) return GP_PIPE;
   }
   const int N = c->P.n_epochs;
-  if (smem_ok && N >= 40) {
-    if (N <= 168) return (S < 512 && N < 80 && c->gp_tile != 0) ? GP_PIPE : GP_SMEM;
-    return S >= 2048 ? GP_BATCH : GP_SMEM;
-  }
+  if (smem_ok && N >= 40 && N <= 208) return (S < 512 && N < 80 && c->gp_tile != 0) ? GP_PIPE : GP_SMEM;
   if (c->gp_tile == 0) return GP_BATCH;
   if (N >= 140 && S >= 512) return GP_BATCH;
   if (!pred && S >= 4096 && N <= 32) return GP_BATCH;
