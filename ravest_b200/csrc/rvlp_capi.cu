@@ -678,6 +678,10 @@ class StagePool {
     // 31 / 25 / 23.5 / 22.7-23.3 ms per call against 21.4 ms device-resident
     unsigned hw = std::thread::hardware_concurrency();
     unsigned n = hw * 3 / 4 > 12 ? 12 : hw * 3 / 4;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) {       // one process per GPU (torchrun): share the host's threads
+      const int lw = atoi(e);
+      if (lw > 1) n = n / (unsigned)lw > 2 ? n / (unsigned)lw : 2;
+    }
     if (const char* e = getenv("RVLP_STAGE_THREADS")) n = (unsigned)atoi(e);
     for (unsigned i = 1; i < n; ++i) {
       try {
