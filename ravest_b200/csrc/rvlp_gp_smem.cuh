@@ -1,4 +1,4 @@
-// rvlp_gp_smem.cuh — K3 for 40..168 epochs (config 5): one 4-warp CTA per sample in flight, the factor in SHARED MEMORY
+// rvlp_gp_smem.cuh — K3 for 40..208 epochs (config 5): one 4-warp CTA per sample in flight, the factor in SHARED MEMORY
 // as 8 x 8 tiles in tensor-core fragment order, the whole O(N^3) part on the fp64 tensor cores.
 //
 // GPLogPosterior.log_probability (/root/reference/src/ravest/fit.py:7836-7901, 8062-8105; kernel gp.py:145-156):
@@ -6,8 +6,8 @@
 //
 // Why another kernel.  rvlp_gp_pipe.cuh keeps the triangle in REGISTERS (6 x 6 tiles, DFMA updates): two samples per
 // SM, a barrier-bound dependency chain, 25 % of the fp64 peak at N = 120.  rvlp_gp_batch.cuh keeps it in HBM and pays
-// ~N^3 / 12 bytes of traffic per sample.  Here the factor (54 KB at N = 120: the strictly lower 8 x 8 tiles) stays in
-// shared memory, THREE samples per SM, and the O(N^3) part is `mma.sync.m8n8k4.f64` (SASS DMMA.8x8x4): one warp
+// ~N^3 / 12 bytes of traffic per sample.  Here the factor (the strictly lower 8 x 8 tiles; 38 KB of shared slots at
+// N = 120, see gps_diag_slots) stays in shared memory, FOUR samples per SM, and the O(N^3) part is `mma.sync.m8n8k4.f64` (SASS DMMA.8x8x4): one warp
 // instruction per 256 FMAs keeps an SM sub-partition's fp64 pipe busy for 16 cycles (latency 26: tools/dmma_lat.cu), so
 // the few warps that fit are enough to feed it.  Left-looking by block column j (NT = ceil(N / 8) of them):
 //   * a tile of L in "A-fragment order" (lane l holds L[l / 4][l % 4] and L[l / 4][4 + l % 4]) serves as the A operand
@@ -23,7 +23,7 @@
 //     alpha_j = W (r_j - sum_k L_jk alpha_k), chi^2, sum ln L_kk and the covariance entries of tile (j + 1, j + 1) (its
 //     Gram sum comes from the worker that owns row j + 1, through a double-buffered hand-over block);
 //   * two named barriers per block column: "W is published" (arrive / sync), "column j is stored".
-// Per sample at N = 120: 1328 DMMA instead of 23.7 k DFMA warp instructions; 0.79 ms per 1e4 samples (1.44 pipelined).
+// Per sample at N = 120: 1328 DMMA instead of 23.7 k DFMA warp instructions; 0.71 ms per 1e4 samples (1.44 pipelined).
 // The mean model / priors / reject flags come from gpb_prologue_kernel (one warp per sample, rvlp_gp_batch.cuh).
 // Deterministic: fixed summation order per tile; the ticket only decides WHICH CTA takes a sample - out[s] depends on
 // (theta[s], epochs) only.  Phase stamps for tuning: -DRVLP_GPS_TRACE + tools/gp_smem_trace.py.
