@@ -255,19 +255,20 @@ static int launch_gp_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doub
 
 // Shared-memory tensor-core Cholesky (rvlp_gp_smem.cuh): one 4-warp CTA per sample in flight; the prologue kernel of
 // the batched path supplies residual / phases / hyperparameters / flags through a small per-sample workspace.
-static int launch_gp_smem(rvlp_ctx* c, const double* theta_dev, int64_t S, double* out_dev, cudaStream_t st) {
+template <bool PRED>
+static int launch_gp_smem(rvlp_ctx* c, const double* theta_dev, int64_t S, double* out_dev, double* beta_dev, cudaStream_t st) {
   DevProblem P = c->P;
   P.epochs_global = 1;
   const int N = P.n_epochs;
   const GpbDims d = gpb_dims(N);
-    const int smem_f = gps_smem_bytes(N);
+    const int smem_f = gps_smem_bytes(N, PRED);
   const int smem_pro = smem_layout(P).total;
   if (smem_f > c->max_smem || smem_pro > c->max_smem)
     return fail(RVLP_EUNSUPPORTED, "shared-memory GP kernel: %d epochs need %d B per CTA (> %d)", N, smem_f, c->max_smem);
   int rc = ensure_pool(c->device);
   if (rc) return rc;
-  void (*kern)(DevProblem, int64_t, GpbWork, unsigned long long*, double*) = gps_factor_kernel;
-  CUDA_TRY(cudaFuncSetAttribute(gpb_prologue_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+  void (*kern)(DevProblem, int64_t, GpbWork, unsigned long long*, double*, double*) = gps_factor_kernel<PRED>;
+  CUDA_TRY(cudaFuncSetAttribute(gpb_prologue_kernel<PRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
   const size_t per = ((size_t)(3 * d.np + 4 + P.n_inst + 4) * 8 + 8 + 255) & ~(size_t)255;
   int64_t chunk = (int64_t)(((size_t)2 << 30) / per);
@@ -303,14 +304,14 @@ static int launch_gp_smem(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
   for (int64_t s0 = 0; s0 < S; s0 += chunk) {
     const int64_t n = S - s0 < chunk ? S - s0 : chunk;
     int grid = 0;
-    if ((rc = grid_for(c->device, (const void*)gpb_prologue_kernel<false>, smem_pro, (n + kWarps - 1) / kWarps, &grid))) return rc;
+    if ((rc = grid_for(c->device, (const void*)gpb_prologue_kernel<PRED>, smem_pro, (n + kWarps - 1) / kWarps, &grid))) return rc;
     CUDA_TRY(cudaMemsetAsync(ticket, 0, 8, st));
-    gpb_prologue_kernel<false><<<grid, kThreads, smem_pro, st>>>(P, theta_dev + s0 * P.ndim, n, w);
+    gpb_prologue_kernel<PRED><<<grid, kThreads, smem_pro, st>>>(P, theta_dev + s0 * P.ndim, n, w);
     if ((rc = grid_for(c->device, (const void*)kern, smem_f, n, &grid, kGsThreads))) return rc;
     if (const char* e = getenv("RVLP_GP_GRID")) {           // tests / experiments: cap the grid
       if (atoi(e) > 0 && atoi(e) < grid) grid = atoi(e);
     }
-    kern<<<grid, kGsThreads, smem_f, st>>>(P, n, w, ticket, out_dev + s0);
+    kern<<<grid, kGsThreads, smem_f, st>>>(P, n, w, ticket, out_dev ? out_dev + s0 : nullptr, beta_dev ? beta_dev + s0 * N : nullptr);
     g_launches += 2;
     CUDA_TRY(cudaGetLastError());
   }
@@ -325,18 +326,21 @@ static int launch_gp_smem(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
 //   under 40 epochs: the pipelined kernel; the batched path for >= 4096 samples at <= 32 epochs;
 //   beyond (one shared-memory CTA per SM from 209 epochs, no pipelined shape from 220): the batched path from 512
 //     samples, the pipelined kernel below while it has a shape.
-//   Conditioning (K7): pipelined up to 139 epochs or under 512 samples, batched beyond.
+//   Conditioning (K7; profiles/r02ak_gp_pred_sweep.log): the shared-memory kernel's <PRED> flavour (whole factor kept,
+//     three samples per SM) at 40..144 epochs (1.9x the pipelined kernel at 120) and to 208 under 2048 samples; the
+//     pipelined kernel below 40 epochs and for small batches under 80; batched beyond.
 // RVLP_GP_KERNEL = pipe | smem | batch forces one (tests, experiments).
 enum { GP_PIPE = 0, GP_SMEM = 1, GP_BATCH = 2 };
 static int gp_choice(const rvlp_ctx* c, int64_t S, bool pred) {
-  const bool smem_ok = !pred && gps_smem_bytes(c->P.n_epochs) <= c->max_smem;
+  const bool smem_ok = gps_smem_bytes(c->P.n_epochs, pred) <= c->max_smem;
   if (const char* e = getenv("RVLP_GP_KERNEL")) {
     if (!strcmp(e, "smem") && smem_ok) return GP_SMEM;
     if (!strcmp(e, "batch")) return GP_BATCH;
     if (!strcmp(e, "pipe") && c->gp_tile != 0) return GP_PIPE;
   }
   const int N = c->P.n_epochs;
-  if (smem_ok && N >= 40 && N <= 208) return (S < 512 && N < 80 && c->gp_tile != 0) ? GP_PIPE : GP_SMEM;
+  if (smem_ok && N >= 40 && N <= (pred ? 144 : 208)) return (S < 512 && N < 80 && c->gp_tile != 0) ? GP_PIPE : GP_SMEM;
+  if (smem_ok && pred && N <= 208 && S < 2048) return GP_SMEM;
   if (c->gp_tile == 0) return GP_BATCH;
   if (N >= 140 && S >= 512) return GP_BATCH;
   if (!pred && S >= 4096 && N <= 32) return GP_BATCH;
@@ -903,7 +907,7 @@ int rvlp_gp_logprob_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, doubl
   cudaStream_t st = (cudaStream_t)stream;
   const int which = gp_choice(c, S, false);
   if (which == GP_BATCH) return launch_gp_batch<false>(c, theta_dev, S, out_dev, nullptr, st);
-  if (which == GP_SMEM) return launch_gp_smem(c, theta_dev, S, out_dev, st);
+  if (which == GP_SMEM) return launch_gp_smem<false>(c, theta_dev, S, out_dev, nullptr, st);
   int grid = 0, rc;
   const char* grid_cap = getenv("RVLP_GP_GRID");          // tests / experiments: cap the grid (e.g. 148 = one CTA per SM)
 #define RVLP_GP_PIPE(TT)                                                                                    \
@@ -966,6 +970,8 @@ int rvlp_gp_predict_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, const
   const int which = gp_choice(c, S, true);
   if (which == GP_BATCH) {
     if ((rc = launch_gp_batch<true>(c, theta_dev, S, chi2_dev, d_beta, st))) return rc;
+  } else if (which == GP_SMEM) {
+    if ((rc = launch_gp_smem<true>(c, theta_dev, S, chi2_dev, d_beta, st))) return rc;
   } else {
     const char* grid_cap = getenv("RVLP_GP_GRID");        // tests / experiments: cap the grid
 #define RVLP_GP_PRED(TT)                                                                                          \

@@ -54,9 +54,12 @@ __host__ __device__ inline int gps_slot_count(int nt) {
   return n;
 }
 __host__ __device__ inline int gps_tab_bytes(int nt) { return (nt * nt * 2 + 15) & ~15; }
-__host__ __device__ inline int gps_smem_bytes(int N) {
+// pred (K7, the conditioning path): beta = L^-T alpha needs the WHOLE factor at the end - every tile keeps its own slot
+// and the inverse of every diagonal tile is kept as well.
+__host__ __device__ inline int gps_tile_slots(int nt, bool pred) { return pred ? nt * (nt - 1) / 2 : gps_slot_count(nt); }
+__host__ __device__ inline int gps_smem_bytes(int N, bool pred = false) {
   const int nt = gps_tile_rows(N), np = nt * 8;
-  return gps_slot_count(nt) * 512 + gps_tab_bytes(nt) + (64 + 8) * 8 + 2 * (64 + 32) * 8 + 6 * np * 8 + 64;
+  return gps_tile_slots(nt, pred) * 512 + gps_tab_bytes(nt) + ((pred ? nt : 1) * 64 + 8) * 8 + 2 * (64 + 32) * 8 + 6 * np * 8 + 64;
 }
 
 __device__ __forceinline__ void gps_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -242,7 +245,7 @@ __device__ __forceinline__ void gps_solve_group(const GpsView& V, double2 w, int
 // (forward substitution on the identity, one step behind the pivots); publishes W = L_jj^-1 in fragment order.  The
 // pivot chain is shuffle -> reciprocal (seed + 3 fp64 operations) -> two multiplies -> shuffle; the reciprocal square
 // roots that scale L and W are off it.  Returns W (accumulator layout) and the product of the pivots.
-__device__ __forceinline__ void gps_factor_diag(const GpsView& V, int lane, double c0, double c1, double& w0, double& w1, double& p8) {
+__device__ __forceinline__ void gps_factor_diag(double* wbuf, int lane, double c0, double c1, double& w0, double& w1, double& p8) {
   const int g = lane >> 2, q = lane & 3, quad = lane & ~3;
   double z0 = g == 2 * q ? 1.0 : 0.0, z1 = g == 2 * q + 1 ? 1.0 : 0.0;
   p8 = 1.0;
@@ -268,22 +271,28 @@ __device__ __forceinline__ void gps_factor_diag(const GpsView& V, int lane, doub
   w0 = z0;
   w1 = z1;
   const int e0 = 2 * (4 * g + ((2 * q) & 3)) + ((2 * q) >> 2), e1 = 2 * (4 * g + ((2 * q + 1) & 3)) + ((2 * q + 1) >> 2);
-  V.ljj[e0] = z0;
-  V.ljj[e1] = z1;
+  wbuf[e0] = z0;
+  wbuf[e1] = z1;
 }
 
 // One kernel for every epoch count that fits (the tile count per worker is a runtime loop).
-__global__ void __launch_bounds__(kGsThreads, RVLP_GPS_MB)
-gps_factor_kernel(DevProblem P, int64_t S, GpbWork w, unsigned long long* __restrict__ ticket, double* __restrict__ out) {
+// PRED (K7, /root/reference/src/ravest/fit.py:7494-7554, 5386-5429): residual without priors (the prologue's <true>
+// flavour), every tile and every diagonal inverse kept, then beta = L^-T alpha by a right-looking blocked back
+// substitution on the fragment-order tiles; out = chi^2 = alpha.alpha (may be null), beta_out [S, N].
+template <bool PRED>
+__global__ void __launch_bounds__(kGsThreads, PRED ? 3 : RVLP_GPS_MB)
+gps_factor_kernel(DevProblem P, int64_t S, GpbWork w, unsigned long long* __restrict__ ticket, double* __restrict__ out,
+                  double* __restrict__ beta_out) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int N = P.n_epochs, NT = gps_tile_rows(N), NP = NT * 8;
   GpsView V;
   V.N = N; V.NT = NT;
-  V.Ls = reinterpret_cast<double2*>(smem);                                 // [gps_slot_count(NT)][32] tile (i, k) at slot tab[i][k]
-  unsigned short* tab_w = reinterpret_cast<unsigned short*>(smem + (size_t)gps_slot_count(NT) * 512);
+  const int n_slots = gps_tile_slots(NT, PRED);
+  V.Ls = reinterpret_cast<double2*>(smem);                                 // [n_slots][32] tile (i, k) at slot tab[i][k]
+  unsigned short* tab_w = reinterpret_cast<unsigned short*>(smem + (size_t)n_slots * 512);
   V.tab = tab_w;
-  V.ljj = reinterpret_cast<double*>(smem + (size_t)gps_slot_count(NT) * 512 + gps_tab_bytes(NT));   // W = L_jj^-1, fragment order
-  V.invd = V.ljj + 64;                                                     // [8]
+  V.ljj = reinterpret_cast<double*>(smem + (size_t)n_slots * 512 + gps_tab_bytes(NT));   // W = L_jj^-1, fragment order (PRED: [NT] of them)
+  V.invd = V.ljj + (PRED ? NT : 1) * 64;                                   // [8] (spare)
   V.dtile = V.invd + 8;                                                    // [2][64 + 32] diagonal-tile hand-over
   V.t = V.dtile + 2 * 96;                                                  // [NP] each
   V.cph = V.t + NP;
@@ -303,9 +312,13 @@ gps_factor_kernel(DevProblem P, int64_t S, GpbWork w, unsigned long long* __rest
     const int i = idx / NT, k = idx - i * NT;
     int slot = 0;
     if (i > k) {
-      const int d = i - k;
-      for (int e = 1; e < d; ++e) slot += gps_diag_slots(NT, e);
-      slot += k % gps_diag_slots(NT, d);
+      if (PRED) {
+        slot = i * (i - 1) / 2 + k;
+      } else {
+        const int d = i - k;
+        for (int e = 1; e < d; ++e) slot += gps_diag_slots(NT, e);
+        slot += k % gps_diag_slots(NT, d);
+      }
     }
     tab_w[idx] = (unsigned short)slot;
   }
@@ -318,7 +331,11 @@ gps_factor_kernel(DevProblem P, int64_t S, GpbWork w, unsigned long long* __rest
     if (s >= S) break;
     const int st = w.status[s];
     if (st != 0) {                                         // CTA-uniform
-      if (tid == 0) {
+      if (PRED) {                                          // the reference raises: NaN rows
+        const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+        for (int i = tid; i < N; i += kGsThreads) beta_out[(size_t)s * N + i] = qnan;
+        if (tid == 0 && out) out[s] = qnan;
+      } else if (tid == 0) {
         double r = -INFINITY;                              // fit.py:7857-7886
         if (st == 2) {                                     // non-finite mean model, fit.py:8082-8083
           r = -INFINITY + w.lp[s] + w.lhp[s];
@@ -378,7 +395,7 @@ gps_factor_kernel(DevProblem P, int64_t S, GpbWork w, unsigned long long* __rest
         GPS_STAMP(3)
         int i = first_row(j);
         if (i < NT) {
-          const double2 wf = *reinterpret_cast<const double2*>(V.ljj + 2 * lane);
+          const double2 wf = *reinterpret_cast<const double2*>(V.ljj + (PRED ? j * 64 : 0) + 2 * lane);
 #pragma unroll 1
           for (; i + kGsWorkers < NT; i += 2 * kGsWorkers) gps_solve_group<2>(V, wf, j, i, kGsWorkers, lane);
           if (i < NT) gps_solve_group<1>(V, wf, j, i, kGsWorkers, lane);
@@ -411,7 +428,7 @@ gps_factor_kernel(DevProblem P, int64_t S, GpbWork w, unsigned long long* __rest
         }
         GPS_STAMP(1)
         double w0, w1, p8;
-        gps_factor_diag(V, lane, c01.x - (e0 + f0), c01.y - (e1 + f1), w0, w1, p8);
+        gps_factor_diag(V.ljj + (PRED ? j * 64 : 0), lane, c01.x - (e0 + f0), c01.y - (e1 + f1), w0, w1, p8);
         __threadfence_block();
         gps_bar_arrive(1, kGsThreads);
         GPS_STAMP(2)
@@ -438,7 +455,49 @@ gps_factor_kernel(DevProblem P, int64_t S, GpbWork w, unsigned long long* __rest
       if (lane == 0) { red_s[0] = chi; red_s[1] = logdet; }
     }
     __syncthreads();
-    if (tid == 0) {
+    if (PRED) {
+      if (tid == 0 && out) out[s] = red_s[0];              // chi^2 = r^T C^-1 r (fit.py:5428-5429)
+      // beta = L^-T alpha, right-looking: beta_i = W_i^T z_i by one warp, then every warp folds beta_i into the z_j of
+      // its tiles (i, j), j < i (fragment order: lane (g, q) holds L[g][q], L[g][4 + q]; the sums over g are three
+      // xor-shuffles).  z lives in V.al and becomes beta in place.
+      const int g = lane >> 2, q = lane & 3;
+#pragma unroll 1
+      for (int i = NT - 1; i >= 0; --i) {
+        if (warp == kGsWorkers) {
+          const double2 wv = *reinterpret_cast<const double2*>(V.ljj + i * 64 + 2 * lane);
+          const double zg = V.al[i * 8 + g];
+          double p0 = wv.x * zg, p1 = wv.y * zg;
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+          }
+          __syncwarp();                                    // every lane has read z_i before it is overwritten
+          if (g == 0) {
+            V.al[i * 8 + q] = p0;
+            V.al[i * 8 + 4 + q] = p1;
+            if (i * 8 + q < N) beta_out[(size_t)s * N + i * 8 + q] = p0;
+            if (i * 8 + 4 + q < N) beta_out[(size_t)s * N + i * 8 + 4 + q] = p1;
+          }
+        }
+        __syncthreads();
+        const double bg = V.al[i * 8 + g];
+        for (int j = warp; j < i; j += kGsWorkers + 1) {
+          const double2 a = gps_tile(V, i, j)[lane];
+          double p0 = a.x * bg, p1 = a.y * bg;
+#pragma unroll
+          for (int o = 4; o < 32; o <<= 1) {
+            p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+          }
+          if (g == 0) {
+            V.al[j * 8 + q] -= p0;
+            V.al[j * 8 + 4 + q] -= p1;
+          }
+        }
+        __syncthreads();
+      }
+    } else if (tid == 0) {
       const double ll = -0.5 * red_s[0] - red_s[1] - 0.5 * (double)N * kLog2Pi;
       double r = ll + w.lp[s] + w.lhp[s];                   // fit.py:7898-7900
       r += P.jacobian;

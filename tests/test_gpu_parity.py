@@ -808,6 +808,24 @@ def test_gp_shared_memory_kernel_is_bit_stable_and_matches_the_oracle(cuda, monk
     for rep in range(5):                                       # a shared-memory race would show up run to run
         again = post.log_probability_batch(th).cpu().numpy()
         assert np.array_equal(again.view(np.int64), base.view(np.int64)), rep
+    # the conditioning flavour of the same kernel (K7: whole factor kept, beta = L^-T alpha on the fragment-order tiles)
+    from oracle import oracle_py
+    pr = oracle_py.Problem(spec)
+    times = np.linspace(spec["time"].min() - 2.0, spec["time"].max() + 2.0, 19)
+    mean, chi2 = post.ctx.gp_predict(th, times, want_chi2=True)
+    mean, chi2 = mean.cpu().numpy(), chi2.cpu().numpy()
+    assert np.isnan(mean[5]).all() and np.isnan(chi2[5]) and np.isnan(mean[9]).all()
+    for i in (0, 1, 2, S - 1):
+        if not np.isfinite(ref[i]):
+            continue
+        mu, c2 = pr.gp_predict(dict(zip(names, map(float, theta[i]))), times)
+        assert np.abs(mean[i] - mu).max() <= 1e-7 * max(1.0, np.abs(mu).max()), (N, i)
+        assert abs(chi2[i] - c2) <= 1e-9 * max(1.0, c2), (N, i)
+    monkeypatch.setenv("RVLP_GP_GRID", "7")
+    mean2, chi22 = post.ctx.gp_predict(th, times, want_chi2=True)
+    monkeypatch.delenv("RVLP_GP_GRID")
+    assert np.array_equal(mean2.cpu().numpy().view(np.int64), mean.view(np.int64))
+    assert np.array_equal(chi22.cpu().numpy().view(np.int64), chi2.view(np.int64))
 
 
 @pytest.mark.gpu
