@@ -1,6 +1,9 @@
 // rvlp_capi.cu — C ABI (include/ravest_b200.h) over the kernels.  No torch, no C++ types
 // across the boundary; errors are integer codes + a thread-local message.
 #include <cuda_runtime.h>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 #include <atomic>
 #include <cstdarg>
@@ -643,6 +646,34 @@ int rvlp_info_criteria_batch(rvlp_ctx* c, const double* theta_dev, int64_t S, in
 // Pageable -> pinned staging copy.  One thread moves ~8 GB/s, which made the NumPy-in path copy-bound (33 ms against a
 // 24 ms kernel at config 3).  A small persistent pool (created on first use, up to 12 threads, never more than three
 // quarters of the host's hardware threads) splits a block into 1 MB slices; the caller copies slices too.
+// memcpy with non-temporal stores: the destination (the pinned staging buffer) is next read by the DMA engine, not by
+// the CPU, so it should not be pulled into the cache first - a regular store's write-allocate makes the copy three
+// memory streams instead of two, which is what bounds the host path when eight ranks stage their shards at once.
+static void stream_copy(char* dst, const char* src, size_t n) {
+#if defined(__x86_64__) && defined(__SSE2__)
+  if (n >= 4096) {
+    const size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+    memcpy(dst, src, head);
+    dst += head; src += head; n -= head;
+    const size_t blocks = n / 64;
+    for (size_t i = 0; i < blocks; ++i) {
+      const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 0);
+      const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 1);
+      const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 2);
+      const __m128i d = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src) + 3);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 0, a);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 1, b);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 2, c);
+      _mm_stream_si128(reinterpret_cast<__m128i*>(dst) + 3, d);
+      src += 64; dst += 64;
+    }
+    _mm_sfence();
+    n -= blocks * 64;
+  }
+#endif
+  memcpy(dst, src, n);
+}
+
 class StagePool {
  public:
   static StagePool& get() {
@@ -650,7 +681,7 @@ class StagePool {
     return *p;
   }
   void copy(char* dst, const char* src, size_t nbytes) {
-    if (n_workers_ == 0 || nbytes < 4 * kSlice) { memcpy(dst, src, nbytes); return; }
+    if (n_workers_ == 0 || nbytes < 4 * kSlice) { stream_copy(dst, src, nbytes); return; }
     auto job = std::make_shared<Job>();      // a late-waking worker keeps ITS job object: it can never touch the next one
     job->dst = dst; job->src = src; job->nbytes = nbytes;
     job->nslices = (nbytes + kSlice - 1) / kSlice;
@@ -701,7 +732,7 @@ class StagePool {
       const size_t i = j.next.fetch_add(1);
       if (i >= j.nslices) break;
       const size_t b = i * kSlice, e = b + kSlice < j.nbytes ? b + kSlice : j.nbytes;
-      memcpy(j.dst + b, j.src + b, e - b);
+      stream_copy(j.dst + b, j.src + b, e - b);
       if (j.pending.fetch_sub(1) == 1) {
         std::lock_guard<std::mutex> lk(j.mu);
         j.done_cv.notify_all();
