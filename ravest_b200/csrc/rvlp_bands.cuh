@@ -150,7 +150,7 @@ __host__ __device__ inline int band_col_stride(int level, int R) { return band_h
 __host__ __device__ inline int band_smem_bytes(int level, int R) {
   return ((kColBlock * band_col_stride(level, R) * 4 + 15) & ~15) + kColBlock * R * (8 + 8 + 4 + 4 + 4) + kColBlock * 8 + 16;
 }
-constexpr int band_mode_of(int level) { return level == 0 ? 0 : (level <= 3 ? 1 : 2); }
+__host__ __device__ constexpr int band_mode_of(int level) { return level == 0 ? 0 : (level <= 3 ? 1 : 2); }
 
 // MODE 0: level 0 (every element counts, one histogram per column, digits cluster -> run-length aggregation);
 // MODE 1: levels 1-3 (prefix and digit live in the key's high word: 32-bit classification);
@@ -162,9 +162,10 @@ constexpr int band_mode_of(int level) { return level == 0 ? 0 : (level <= 3 ? 1 
 #ifndef RVLP_BAND_MINB1
 #define RVLP_BAND_MINB1 3      // levels 1-3: 8 loads in flight per thread (80 registers) beat a 4th resident CTA
 #endif
+// (the body takes the row-slab index / count as arguments: band_fallback_kernel runs all levels in one CTA per column block)
 template <int MODE>
-__global__ void __launch_bounds__(kBandThreads, (MODE == 0 ? RVLP_BAND_MINB0 : RVLP_BAND_MINB1))
-band_level_kernel(const double* __restrict__ A, int64_t S, int64_t T, int level, BandTargets tg, BandWorkspace W) {
+__device__ __forceinline__ void band_level_body(const double* __restrict__ A, int64_t S, int64_t T, int level, const BandTargets& tg,
+                                                const BandWorkspace& W, const int slab, const int n_slabs) {
   extern __shared__ __align__(16) unsigned char bsm[];
   const int R = 2 * tg.n_q;
   const int HS = band_hist_slots(level, R);
@@ -181,7 +182,7 @@ band_level_kernel(const double* __restrict__ A, int64_t S, int64_t T, int level,
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t c0 = (int64_t)blockIdx.x * kColBlock;
   const int ncol = (int)min((int64_t)kColBlock, T - c0);
-  const bool writer = blockIdx.y == 0;
+  const bool writer = slab == 0;
 
   // columns collected by an EARLIER launch are finished as far as this kernel is concerned (a value equal to
   // `level` can only be this launch's own writer CTA racing ahead: recompute, the decision is the same)
@@ -271,8 +272,8 @@ band_level_kernel(const double* __restrict__ A, int64_t S, int64_t T, int level,
   // ---- 2. one pass over this CTA's slab of rows (software-pipelined: the next U loads are in flight while
   //         the current U elements are classified)
   const int c = tid % kColBlock, rl = tid / kColBlock;
-  const int64_t rows_per = (S + gridDim.y - 1) / gridDim.y;
-  const int64_t r_begin = (int64_t)blockIdx.y * rows_per, r_end = min(S, r_begin + rows_per);
+  const int64_t rows_per = (S + n_slabs - 1) / n_slabs;
+  const int64_t r_begin = (int64_t)slab * rows_per, r_end = min(S, r_begin + rows_per);
   bool saw_nan = false;
   const int my_mode = c < ncol ? mode_s[c] : -2;
   if (my_mode != -2) {
@@ -380,17 +381,23 @@ band_level_kernel(const double* __restrict__ A, int64_t S, int64_t T, int level,
   }
 }
 
+template <int MODE>
+__global__ void __launch_bounds__(kBandThreads, (MODE == 0 ? RVLP_BAND_MINB0 : RVLP_BAND_MINB1))
+band_level_kernel(const double* __restrict__ A, int64_t S, int64_t T, int level, BandTargets tg, BandWorkspace W) {
+  band_level_body<MODE>(A, S, T, level, tg, W, (int)blockIdx.y, (int)gridDim.y);
+}
+
 // Finishing kernel: one warp per column.  Streaming columns have complete keys in prefix[8]; collected columns
 // run their remaining levels on the candidates (cached in shared memory).  Then numpy's blend.
 constexpr int kFinishSmem = kBandWarps * (kCandCap * 8 + 256 * 4);
-__global__ void __launch_bounds__(kBandThreads)
-band_finish_kernel(int64_t T, BandTargets tg, BandWorkspace W, double* __restrict__ out) {
+__device__ __forceinline__ void band_finish_body(int64_t T, const BandTargets& tg, const BandWorkspace& W, double* __restrict__ out,
+                                                 int64_t col_block) {
   extern __shared__ __align__(16) unsigned char bsm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* cand_s = reinterpret_cast<double*>(bsm) + warp * kCandCap;
   uint32_t* hist_w = reinterpret_cast<uint32_t*>(bsm + kBandWarps * kCandCap * 8) + warp * 256;
   const int R = 2 * tg.n_q;
-  const int64_t c = (int64_t)blockIdx.x * kBandWarps + warp;
+  const int64_t c = col_block * kBandWarps + warp;
   if (c >= T) return;
   const int mode = W.mode[c];
   if (mode == kModeFastDone) return;                       // warp-uniform: the column's result is already in `out`
@@ -436,6 +443,37 @@ band_finish_kernel(int64_t T, BandTargets tg, BandWorkspace W, double* __restric
       out[(size_t)q * T + c] = res;
     }
   }
+}
+
+__global__ void __launch_bounds__(kBandThreads)
+band_finish_kernel(int64_t T, BandTargets tg, BandWorkspace W, double* __restrict__ out) {
+  band_finish_body(T, tg, W, out, (int64_t)blockIdx.x);
+}
+
+// After the two-pass path (rvlp_bands_fast.cuh): the columns it could not finish (target bins that do not fit the
+// candidate buffer: heavy ties, adversarial data) take the radix path here - ONE launch, one CTA per column block over
+// ALL rows, so that the levels need no grid-wide dependency and run back to back inside the kernel; a CTA whose
+// columns are all finished returns at once (the usual case: ~3 us instead of ten launches).  Same bodies, same bits.
+static_assert(kColBlock == kBandWarps, "band_fallback_kernel finishes its column block with one warp per column");
+__global__ void __launch_bounds__(kBandThreads, 2)
+band_fallback_kernel(const double* __restrict__ A, int64_t S, int64_t T, BandTargets tg, BandWorkspace W, double* __restrict__ out) {
+  __shared__ int todo_s;
+  const int64_t c0 = (int64_t)blockIdx.x * kColBlock;
+  if (threadIdx.x == 0) {
+    int todo = 0;
+    for (int c = 0; c < kColBlock && c0 + c < T; ++c) todo |= W.mode[c0 + c] != kModeFastDone;
+    todo_s = todo;
+  }
+  __syncthreads();
+  if (!todo_s) return;
+  for (int level = 0; level <= kLevels; ++level) {
+    if (band_mode_of(level) == 0) band_level_body<0>(A, S, T, level, tg, W, 0, 1);
+    else if (band_mode_of(level) == 1) band_level_body<1>(A, S, T, level, tg, W, 0, 1);
+    else band_level_body<2>(A, S, T, level, tg, W, 0, 1);
+    __threadfence();
+    __syncthreads();
+  }
+  band_finish_body(T, tg, W, out, (int64_t)blockIdx.x);
 }
 
 }  // namespace rvlp

@@ -14,8 +14,8 @@
 //      candidate buffer;
 //   3. finish: exact selection of the remaining rank among the candidates of the target's bin, numpy's `_lerp`.
 // The result is the exact order statistic - bit-identical to numpy - for ANY data; only the speed depends on the
-// sample.  A column whose target bins do not fit the buffer (heavy ties, adversarial data) is left to the radix path,
-// which runs afterwards and skips every column finished here.  Constant samples (a == b, e.g. an all-zero trend
+// sample.  A column whose target bins do not fit the buffer (heavy ties, adversarial data) is left to the radix path
+// (band_fallback_kernel, rvlp_bands.cuh: one launch afterwards, skips every column finished here).  Constant samples (a == b, e.g. an all-zero trend
 // column) use the three bins <a, ==a, >a and need no candidates when the targets fall on the constant.
 // HBM: 2 x S x T x 8 bytes + 1 % for the sample; integer counting only, so the bits do not depend on the grid.
 #pragma once

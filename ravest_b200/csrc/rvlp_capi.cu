@@ -1091,6 +1091,8 @@ int rvlp_percentile_columns(const double* A_dev, int64_t S, int64_t T, const dou
     CUDA_TRY(cudaFuncSetAttribute(band_level_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(1, kMaxTargets)));
     CUDA_TRY(cudaFuncSetAttribute(band_level_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, band_smem_bytes(1, kMaxTargets)));
     CUDA_TRY(cudaFuncSetAttribute(band_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFinishSmem));
+    CUDA_TRY(cudaFuncSetAttribute(band_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  std::max(band_smem_bytes(1, kMaxTargets), kFinishSmem)));
     CUDA_TRY(cudaFuncSetAttribute(band_fast_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kColBlock * (kFastBins + 1) * 4));
     CUDA_TRY(cudaFuncSetAttribute(band_fast_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kColBlock * (kFastBins + 1) * 4));
     CUDA_TRY(cudaFuncSetAttribute(band_fast_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFastFinishSmem));
@@ -1137,8 +1139,11 @@ int rvlp_percentile_columns(const double* A_dev, int64_t S, int64_t T, const dou
       }
     }
     band_fast_finish_kernel<<<(unsigned)T, kBandThreads, kFastFinishSmem, st>>>(T, tg, W, F, out_dev);
-    g_launches += 5;
+    // what the two passes could not finish: the radix path, one launch (a CTA per column block, all levels inside)
+    band_fallback_kernel<<<(unsigned)ncb, kBandThreads, std::max(band_smem_bytes(1, R), kFinishSmem), st>>>(A_dev, S, T, tg, W, out_dev);
+    g_launches += 6;
     CUDA_TRY(cudaGetLastError());
+    return RVLP_OK;
   }
   for (int level = 0; level <= kLevels; ++level) {
     // Row split: every CTA does the same amount of work, so the grid is sized to ONE wave of resident CTAs
