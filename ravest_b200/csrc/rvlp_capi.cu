@@ -404,6 +404,11 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
   }
   P.n_pad = (int)((n_epochs + kPadTo - 1) / kPadTo * kPadTo);
   while (P.batch_cap > kG && smem_layout(P).total > 74 * 1024) --P.batch_cap;   // keep three CTAs per SM possible
+  {
+    int64_t units = (int64_t)P.n_pad * (P.n_planets > 0 ? P.n_planets : 1), gu = kGssUnits;
+    if (const char* e = getenv("RVLP_GSS_UNITS")) gu = atoll(e) > 0 ? atoll(e) : gu;   // experiments (tools/k1_shard.py)
+    P.gss_min = (int)((gu + units - 1) / units);
+  }
 
   // packed, padded epoch block: [t | vel | velerr^2] doubles + int32 instrument ids
   std::vector<unsigned char> blk((size_t)P.n_pad * 28);

@@ -21,6 +21,10 @@ namespace rvlp {
 #ifndef RVLP_W
 #define RVLP_W 4
 #endif
+#ifndef RVLP_GSS_DIV
+#define RVLP_GSS_DIV 2   // guided self-scheduling: a grab is (samples left) / (RVLP_GSS_DIV x warps), see logprob_kernel
+#endif
+constexpr int kGssUnits = 4096;   // least work (sample x epoch x planet units) in a grab of the guided schedule
 #ifndef RVLP_MIN_BLOCKS
 #define RVLP_MIN_BLOCKS 2
 #endif
@@ -55,6 +59,7 @@ struct DevProblem {
   int n_planets, par, n_inst, ndim, n_priors, n_hyper, n_model, n_epochs, n_pad;
   int epochs_global;   // 1: too many epochs for shared memory - the kernels read them from global memory (L1 / L2)
   int batch_cap;       // samples a warp can take through the prologue together (>= kG; sizes the per-warp scratch)
+  int gss_min;         // smallest grab of K1's guided schedule: about kGssUnits units of work (1 sample at config 3)
   double t0, jacobian, renorm;
   const int32_t* src_col;
   const double* src_const;
@@ -527,27 +532,39 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
   // nb = samples per prologue batch (1..batch_cap): small launches use 1 so that every warp gets a sample, large
   // ones as many as fill the lanes of the (sample, planet) and (sample, prior) phases; the bits of a sample's
   // result do not depend on it.
-  const int64_t n_batches = (S + nb - 1) / nb;
   const int64_t gw = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
 #if RVLP_STAGGER_NS > 0
   if ((warp >> 2) & 1) __nanosleep(RVLP_STAGGER_NS);
 #endif
 
-  // Every warp starts on batch `gw`; further batches come from a global ticket counter when the launch has
-  // several batches per warp (no quantisation tail: 13.2 batches per warp would otherwise cost 14), or from a
-  // static stride for small launches.  Which warp evaluates a sample never changes its bits.
-  for (int64_t b = gw; b < n_batches;) {
-    const int64_t s0 = b * nb;
+  // Every warp starts on the batch of `nb` samples at gw * nb.  When the launch has several batches per warp the
+  // further ones come from a global SAMPLE counter by guided self-scheduling: a grab is `nb` samples while plenty
+  // are left and shrinks to (what is left) / (RVLP_GSS_DIV x warps), down to P.gss_min samples (about 4096 units of work: one
+  // sample at config 3, no shrinking at all for 120-epoch data, whose prologue wants full batches), so the launch's
+  // tail is one sample's work instead of one batch's (6 samples x 5000 units at config 3: 0.15 ms of a 2.7 ms
+  // shard, profiles/r02ap_k1_guided_schedule.log).
+  // What is left is estimated from the end of the warp's own previous grab - an upper bound, the counter only
+  // moves on.  Small launches use a static stride.  Which warp evaluates a sample, and in a batch of what size,
+  // never changes its bits.
+  const int64_t s_static = nw * nb;                          // the samples dealt out statically
+  const int nmin = P.gss_min < 1 ? 1 : (P.gss_min < nb ? P.gss_min : nb);
+  int n = nb;
+  for (int64_t s0 = gw * nb; s0 < S;) {
+    const int n_cur = n;
+    const int64_t s_cur = s0;
     if (next_batch) {
+      const int64_t seen = s_cur + n_cur > s_static ? s_cur + n_cur : s_static;
+      const int64_t share = (S - seen) / (RVLP_GSS_DIV * nw);
+      n = share >= nb ? nb : (share < nmin ? nmin : (int)share);
       unsigned long long t = 0;
-      if (lane == 0) t = atomicAdd(next_batch, 1ull);
-      b = nw + (int64_t)__shfl_sync(0xffffffffu, t, 0);
+      if (lane == 0) t = atomicAdd(next_batch, (unsigned long long)n);
+      s0 = s_static + (int64_t)__shfl_sync(0xffffffffu, t, 0);
     } else {
-      b += nw;
+      s0 += s_static;
     }
-    sample_prologue(P, T, theta, s0, S, scratch, rec, lane, true, nb, pv);
-    for (int g = 0; g < nb; ++g) {
-      const int64_t s = s0 + g;
+    sample_prologue(P, T, theta, s_cur, S, scratch, rec, lane, true, n_cur, pv);
+    for (int g = 0; g < n_cur; ++g) {
+      const int64_t s = s_cur + g;
       if (s >= S) break;
       const double* sr = scratch + g * rec;
       const int flags = __double2loint(sr[1]);
@@ -630,23 +647,29 @@ rv_matrix_kernel(DevProblem P, const double* __restrict__ theta, int64_t S,
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int rec = sample_rec_doubles(P.n_planets, P.n_inst);
   double* scratch = reinterpret_cast<double*>(smem + L.off_scratch) + warp * kG * rec;
-  const int64_t n_batches = (S + kG - 1) / kG;
   const int64_t gw = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
   const int only = component >= 0 ? component : (component == RVLP_RV_TREND ? P.n_planets : -1);
   const bool trend = component < 0;
 
-  for (int64_t b = gw; b < n_batches;) {
-    const int64_t s0 = b * kG;
-    if (next_batch) {                                        // dynamic schedule, as in logprob_kernel
+  const int64_t s_static = nw * kG;                          // guided self-scheduling, as in logprob_kernel
+  const int nmin = T_n * (only < 0 ? P.n_planets : 1) >= kGssUnits / 4 ? 1 : kG;   // short rows: whole batches only
+  int n = kG;
+  for (int64_t s0 = gw * kG; s0 < S;) {
+    const int n_cur = n;
+    const int64_t s_cur = s0;
+    if (next_batch) {
+      const int64_t seen = s_cur + n_cur > s_static ? s_cur + n_cur : s_static;
+      const int64_t share = (S - seen) / (RVLP_GSS_DIV * nw);
+      n = share >= kG ? kG : (share < nmin ? nmin : (int)share);
       unsigned long long t = 0;
-      if (lane == 0) t = atomicAdd(next_batch, 1ull);
-      b = nw + (int64_t)__shfl_sync(0xffffffffu, t, 0);
+      if (lane == 0) t = atomicAdd(next_batch, (unsigned long long)n);
+      s0 = s_static + (int64_t)__shfl_sync(0xffffffffu, t, 0);
     } else {
-      b += nw;
+      s0 += s_static;
     }
-    sample_prologue(P, T, theta, s0, S, scratch, rec, lane, false, kG, nullptr);
-    for (int g = 0; g < kG; ++g) {
-      const int64_t s = s0 + g;
+    sample_prologue(P, T, theta, s_cur, S, scratch, rec, lane, false, n_cur, nullptr);
+    for (int g = 0; g < n_cur; ++g) {
+      const int64_t s = s_cur + g;
       if (s >= S) break;
       const double* sr = scratch + g * rec;
       const double* planets = sr + kHdr + 2 * P.n_inst;
