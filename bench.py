@@ -482,7 +482,11 @@ def main() -> None:
         gathered = [None]
 
         if scaling == "strong":
-            def step():            # the product's multi-GPU entry: evaluate this rank's block, ONE all-gather
+            def step():            # the product's multi-GPU entry: this rank's block, gather fused into the kernel
+                gathered[0] = rdist.sharded_logprob(lambda t: ctx.logprob(t, out=part), th, n_samples=S,
+                                                    theta_is_local=True, ctx=ctx, copy=False)
+
+            def step_nccl():       # the same with ONE NCCL all-gather after the kernel (the fallback without CUDA IPC)
                 gathered[0] = rdist.sharded_logprob(lambda t: ctx.logprob(t, out=part), th, n_samples=S, theta_is_local=True)
         else:
             recv = torch.empty(S * world, dtype=torch.float64, device="cuda") if world > 1 else None
@@ -506,6 +510,16 @@ def main() -> None:
         launches = ravest_b200.launch_count() - n0 - warmup
         clocks = sampler.stop() if sampler else None
         ms_kernel = time_kernel(torch, lambda: ctx.logprob(th, out=part), steps, 1, barrier, flush)
+        gather = None
+        if scaling == "strong" and world > 1:
+            pgs = [g for g in getattr(ctx, "_peer_gathers", {}).values()]
+            fused = bool(pgs) and all(g is not None for g in pgs)
+            ms_nccl = time_kernel(torch, step_nccl, steps, warmup, barrier, flush)
+            step()                                                   # leave the fused result in gathered[0] for the bit check
+            timed_out = any(g.timed_out() for g in pgs if g is not None)
+            gather = {"how": ("fused into the kernel: NVLink peer stores into every rank's vector (CUDA IPC) + a one-warp "
+                              "flag barrier, no collective launch") if fused else "one NCCL all_gather_into_tensor (CUDA IPC refused)",
+                      "ms_per_step_nccl_all_gather": ms_nccl / steps, "barrier_timed_out": timed_out}
         l2_note = (f"theta is {theta.nbytes / 1e6:.0f} MB per GPU (> 126 MB L2), streamed once per step" if flush is None else
                    f"theta is {theta.nbytes / 1e6:.0f} MB per GPU: L2 flushed between the timed iterations (a {2 * L2_BYTES >> 20} MB "
                    f"buffer rewritten outside the per-iteration event pairs)")
@@ -526,10 +540,12 @@ def main() -> None:
         pinned = torch.as_tensor(theta).pin_memory().numpy()
         e2e_pinned_ms = time_host(torch, lambda: ctx.logprob_host(pinned, host_out), steps, 2, barrier)
         ms, ms_kernel, e2e_ms, e2e_pinned_ms = max_over_ranks(ms, ms_kernel, e2e_ms, e2e_pinned_ms)
+        if gather:
+            gather["ms_per_step_nccl_all_gather"] = max_over_ranks(gather["ms_per_step_nccl_all_gather"])[0]
         return dict(spec=spec, theta=theta, theta_all=theta_all, post=post, units=units, total=total, ms=ms,
                     ms_kernel=ms_kernel, e2e_ms=e2e_ms, e2e_pinned_ms=e2e_pinned_ms, launches=launches, clocks=clocks,
                     bit_identical=bit_identical, same=bool(same), rows_local=hi - lo, steps=steps, warmup=warmup,
-                    part=part, l2_note=l2_note)
+                    part=part, l2_note=l2_note, gather=gather)
 
     primary = measure(args.scaling, args.steps, args.warmup, True)
     other_mode = None
@@ -595,6 +611,8 @@ def main() -> None:
         }
         if m["bit_identical"] is not None:
             line["bit_identical_across_ranks"] = m["bit_identical"]
+            if m.get("gather"):
+                line["gather"] = m["gather"]
         if other_mode is not None:
             o = other_mode
             key = "weak_scaling" if args.scaling == "strong" else "strong_scaling"

@@ -30,7 +30,8 @@ EXPORTS = [
     "rvlp_kepler_rv", "rvlp_planet_rv", "rvlp_trend_rv", "rvlp_convert_to_default", "rvlp_prior_eval",
     "rvlp_measure_fp64_peak", "rvlp_launch_count", "rvlp_rv_batch_frozen", "rvlp_walker_check_batch",
     "rvlp_gp_predict_batch", "rvlp_percentile_workspace_bytes", "rvlp_percentile_columns", "rvlp_ctx_autotune", "rvlp_ctx_set_variant",
-    "rvlp_info_criteria_batch",
+    "rvlp_info_criteria_batch", "rvlp_logprob_batch_peers", "rvlp_peer_barrier", "rvlp_peer_alloc", "rvlp_peer_open",
+    "rvlp_peer_close", "rvlp_peer_free",
 ]
 MAX_FROZEN = 16
 MAX_PERCENTILES = 8
@@ -82,6 +83,12 @@ def load() -> C.CDLL:
     lib.rvlp_ctx_destroy.restype = None
     lib.rvlp_logprob_batch.argtypes = [vp, vp, i64, vp, vp]
     lib.rvlp_logprob_batch_host.argtypes = [vp, vp, i64, vp]
+    lib.rvlp_logprob_batch_peers.argtypes = [vp, vp, i64, vp, i32, i64, vp]
+    lib.rvlp_peer_barrier.argtypes = [C.c_int, vp, i32, i32, C.c_uint64, vp]
+    lib.rvlp_peer_alloc.argtypes = [C.c_int, i64, C.POINTER(vp), vp]
+    lib.rvlp_peer_open.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    lib.rvlp_peer_close.argtypes = [C.c_int, vp]
+    lib.rvlp_peer_free.argtypes = [C.c_int, vp]
     lib.rvlp_logprob_parts_batch.argtypes = [vp, vp, i64, vp, vp, vp]
     lib.rvlp_rv_batch.argtypes = [vp, vp, i64, vp, i64, i32, vp, vp]
     lib.rvlp_gp_logprob_batch.argtypes = [vp, vp, i64, vp, vp]

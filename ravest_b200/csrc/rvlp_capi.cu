@@ -114,7 +114,7 @@ int simple_grid(int64_t n) {
 }  // namespace
 
 // K1 shapes (rvlp_kernels.cuh: logprob_kernel<W, MB>); variant 0 is the default until rvlp_ctx_autotune ran
-typedef void (*k1_fn)(DevProblem, const double*, int64_t, double*, double*, double*, int, unsigned long long*);
+typedef void (*k1_fn)(DevProblem, const double*, int64_t, double*, double*, double*, int, unsigned long long*, PeerOut);
 // 0: logprob_kernel<4, 2>   1: logprob_kernel<2, 3>
 constexpr int kK1Variants = 2;
 struct K1Shape {
@@ -522,8 +522,10 @@ void rvlp_ctx_destroy(rvlp_ctx* c) {
 }
 
 static int launch_logprob(rvlp_ctx* c, const double* theta, int64_t S, double* out, double* ll, double* lp,
-                          cudaStream_t st) {
+                          cudaStream_t st, const PeerOut* peer_out = nullptr) {
   if (S == 0) return RVLP_OK;
+  PeerOut peers{};
+  if (peer_out) peers = *peer_out;
   int grid = 0;
   SmemLayout L = smem_layout(c->P);
   K1Shape shape = k1_shape(c->k1, c->P, L);
@@ -545,13 +547,86 @@ static int launch_logprob(rvlp_ctx* c, const double* theta, int64_t S, double* o
     unsigned long long* tickets = c->d_tickets + slot;
     CUDA_TRY(cudaStreamWaitEvent(st, c->ticket_ev[slot], 0));   // the slot's previous user (any stream) has finished
     CUDA_TRY(cudaMemsetAsync(tickets, 0, sizeof(unsigned long long), st));
-    kern<<<grid, shape.threads, smem, st>>>(c->P, theta, S, out, ll, lp, nb, tickets);
+    kern<<<grid, shape.threads, smem, st>>>(c->P, theta, S, out, ll, lp, nb, tickets, peers);
     ++g_launches;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->ticket_ev[slot], st));
     return RVLP_OK;
   }
-  kern<<<grid, shape.threads, smem, st>>>(c->P, theta, S, out, ll, lp, nb, nullptr);
+  kern<<<grid, shape.threads, smem, st>>>(c->P, theta, S, out, ll, lp, nb, nullptr, peers);
+  ++g_launches;
+  CUDA_TRY(cudaGetLastError());
+  return RVLP_OK;
+}
+
+// ------------------------------------------------------------------ fused all-gather over peer memory
+int rvlp_peer_alloc(int device, int64_t bytes, void** dev_ptr, void* handle64) {
+  if (!dev_ptr || !handle64 || bytes <= 0) return fail(RVLP_EINVAL, "bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  DeviceGuard guard(device);
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, (size_t)bytes));
+  cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(RVLP_ECUDA, "rvlp_peer_alloc: %s", cudaGetErrorString(e));
+  }
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return RVLP_OK;
+}
+
+int rvlp_peer_open(int device, const void* handle64, void** dev_ptr) {
+  if (!dev_ptr || !handle64) return fail(RVLP_EINVAL, "bad arguments");
+  DeviceGuard guard(device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *dev_ptr = p;
+  return RVLP_OK;
+}
+
+int rvlp_peer_close(int device, void* dev_ptr) {
+  DeviceGuard guard(device);
+  if (dev_ptr) CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  return RVLP_OK;
+}
+
+int rvlp_peer_free(int device, void* dev_ptr) {
+  DeviceGuard guard(device);
+  if (dev_ptr) CUDA_TRY(cudaFree(dev_ptr));
+  return RVLP_OK;
+}
+
+int rvlp_logprob_batch_peers(rvlp_ctx* c, const double* theta_dev, int64_t S, double* const* outs, int32_t n_outs,
+                             int64_t row_offset, void* stream) {
+  if (!c || S < 0 || !outs || n_outs < 1 || n_outs > kMaxPeers || row_offset < 0 || (S > 0 && !theta_dev))
+    return fail(RVLP_EINVAL, "bad arguments");
+  if (c->P.n_hyper) return fail(RVLP_EINVAL, "GP context: the fused gather serves rvlp_logprob_batch only");
+  DeviceGuard guard(c->device);
+  PeerOut po{};
+  po.n = n_outs;
+  po.off = row_offset;
+  for (int i = 0; i < n_outs; ++i) {
+    if (!outs[i]) return fail(RVLP_EINVAL, "null output pointer %d", i);
+    po.p[i] = outs[i];
+  }
+  return launch_logprob(c, theta_dev, S, nullptr, nullptr, nullptr, (cudaStream_t)stream, &po);
+}
+
+int rvlp_peer_barrier(int device, void* const* flag_blocks, int32_t n_ranks, int32_t my_rank, uint64_t epoch,
+                      void* stream) {
+  if (!flag_blocks || n_ranks < 1 || n_ranks > kMaxPeers || my_rank < 0 || my_rank >= n_ranks)
+    return fail(RVLP_EINVAL, "bad arguments");
+  DeviceGuard guard(device);
+  PeerOut fl{};
+  fl.n = n_ranks;
+  for (int i = 0; i < n_ranks; ++i) fl.p[i] = reinterpret_cast<double*>(flag_blocks[i]);
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(fl, my_rank, (unsigned long long)epoch);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return RVLP_OK;

@@ -67,6 +67,16 @@ struct DevProblem {
   const double* epochs;   // [t | vel | err2] x n_pad doubles, then n_pad int32 instrument ids
 };
 
+// Fused all-gather (multi-GPU): K1 stores a sample's log-probability straight into the gathered [S]
+// vector of EVERY rank - p[i] is rank i's buffer, mapped into this process by CUDA IPC, NVLink peer stores of
+// 8 bytes per sample - at row off + s, instead of a local vector that a collective copies afterwards.
+constexpr int kMaxPeers = 8;
+struct PeerOut {
+  int n;                  // 0: not in use
+  long long off;          // this rank's first row in the gathered vector
+  double* p[kMaxPeers];
+};
+
 constexpr int kHdr = 6;           // sample record header doubles
 __host__ __device__ inline int sample_rec_doubles(int n_planets, int n_inst) {
   return kHdr + 2 * n_inst + kPlanetRec * n_planets;
@@ -519,7 +529,7 @@ template <int W, int MB, bool GE>
 __global__ void __launch_bounds__(kThreads, MB)
 logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double* __restrict__ out,
                double* __restrict__ ll_out, double* __restrict__ lp_out, int nb,
-               unsigned long long* __restrict__ next_batch) {
+               unsigned long long* __restrict__ next_batch, PeerOut peers) {
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = smem_layout(P);
   stage_problem(P, L, smem);
@@ -616,7 +626,7 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
         }
         ll = -0.5 * chi_finish(acc);
       }
-      if (lane == 0) {
+      if (lane == 0 || lane < peers.n) {                    // every lane holds ll (xor-butterfly) and reads lp
         double r;
         if (flags & (F_JIT | F_PRIOR | F_HYPER)) {
           r = -INFINITY;                                     // fit.py:3468, 3480-3482
@@ -625,9 +635,12 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
           r += P.jacobian;
           r += P.renorm;
         }
-        if (out) out[s] = r;
-        if (ll_out) ll_out[s] = ll;
-        if (lp_out) lp_out[s] = lp;
+        if (lane < peers.n) peers.p[lane][peers.off + s] = r;   // lane i -> rank i's gathered vector (peer store)
+        if (lane == 0) {
+          if (out) out[s] = r;
+          if (ll_out) ll_out[s] = ll;
+          if (lp_out) lp_out[s] = lp;
+        }
       }
     }
     __syncwarp();
@@ -849,6 +862,32 @@ __global__ void prior_kernel(rvlp_prior pr, const double* __restrict__ x, int64_
 // Dependent-free DFMA loop: 8 independent chains per thread, 2 flops per DFMA, in the fastest operand form
 // measured on B200 (tools/pipe_probe2.cu: DFMA R,R,R,c issues every 2.08 cycles per SMSP; with three register
 // operands it drops to one per 3.06 cycles - register-file bandwidth).
+// Cross-rank barrier after a launch with PeerOut (one warp; thread i talks to rank i).  The launch before it on the
+// stream has completed, so its peer stores are performed; thread i then publishes `epoch` in rank i's flag word for
+// this rank (release, system scope) and waits until rank i's epoch has arrived in this rank's own flag block
+// (acquire).  Kernels queued after it on the stream may read the gathered vector.  The wait is bounded (~2 s):
+// a rank that never arrives sets flags_self[kMaxPeers] = 1 instead of hanging the GPU.
+__global__ void peer_barrier_kernel(PeerOut flags, int my_rank, unsigned long long epoch) {
+  const int i = threadIdx.x;
+  if (i >= flags.n) return;
+  unsigned long long* theirs = reinterpret_cast<unsigned long long*>(flags.p[i]) + my_rank;
+  volatile unsigned long long* mine = reinterpret_cast<unsigned long long*>(flags.p[my_rank]) + i;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+    if (v >= epoch) break;
+    if (clock64() - t0 > 4000000000ll) {
+      reinterpret_cast<unsigned long long*>(flags.p[my_rank])[kMaxPeers] = 1ull;
+      break;
+    }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
          x7 = x0 + 7;

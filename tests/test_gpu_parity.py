@@ -390,6 +390,28 @@ def test_bit_stability_under_sharding_and_batching(cuda):
     assert np.array_equal(host.view(np.int64), full.cpu().numpy().view(np.int64))
 
 
+def test_guided_schedule_covers_every_row(cuda):
+    """K1 / K2 deal samples out by guided self-scheduling (grabs shrink towards the end of a launch): every row must be
+    written, with the bits of a static, one-batch-per-warp launch, for row counts around the schedule's boundaries."""
+    from ravest_b200 import workloads
+    spec, theta = workloads.make_multiplanet(5, 1000, 40_000, seed=77, invalid_frac=0.02)   # 5000 units a row: floor = 1 row
+    post = _post(spec)
+    th = cuda.as_tensor(theta, device="cuda")
+    ref = cuda.cat([post.ctx.logprob(th[i:i + 1000].contiguous()) for i in range(0, len(theta), 1000)])   # static launches
+    for v in (0, 1):
+        post.ctx.set_variant(v)
+        for S in (4735, 4737, 9472, 14209, 28417, 40_000):
+            out = cuda.full((S,), 12345.0, dtype=cuda.float64, device="cuda")
+            post.ctx.logprob(th[:S].contiguous(), out=out)
+            assert not bool((out == 12345.0).any()), (v, S)
+            assert cuda.equal(out.view(cuda.int64), ref[:S].view(cuda.int64)), (v, S)
+    times = np.linspace(0.0, 900.0, 1100)
+    S = 20_000
+    full = post.ctx.rv_matrix(th[:S].contiguous(), times, -2)
+    parts = cuda.cat([post.ctx.rv_matrix(th[i:i + 500].contiguous(), times, -2) for i in range(0, S, 500)])
+    assert cuda.equal(cuda.nan_to_num(full, nan=-7.0).view(cuda.int64), cuda.nan_to_num(parts, nan=-7.0).view(cuda.int64))
+
+
 def test_kernel_shapes_are_bit_identical_and_autotune_picks_one(cuda):
     """logprob_kernel<4, 2> and <2, 3> (rvlp_ctx_autotune chooses between them) must agree bit for bit."""
     from ravest_b200 import workloads
