@@ -128,14 +128,14 @@ int rvlp_logprob_batch(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples
  * same call with the all-gather FUSED into the kernel.  outs[i] (i < n_outs <= 8) is rank i's gathered [S_total]
  * vector, mapped into this process (rvlp_peer_open); every log-probability of this rank's block goes to
  * outs[i][row_offset + s] of every rank by an NVLink peer store.  rvlp_peer_barrier, queued after it on the same
- * stream, publishes this rank's arrival in every rank's flag block and waits (on the device, bounded to ~2 s; a
+ * stream, publishes this rank's arrival in every rank's flag block and waits (on the device, at most timeout_ms; a
  * timeout sets word [8] of this rank's flag block) until every rank has arrived: what follows on the stream may
  * read the gathered vector.  The reference has no counterpart (emcee's pool maps walkers over processes,
  * fit.py:1069-1075); ravest_b200/dist.py drives it and falls back to one NCCL all-gather when IPC is refused. */
 int rvlp_logprob_batch_peers(rvlp_ctx* ctx, const double* theta_dev, int64_t n_samples, double* const* outs,
                              int32_t n_outs, int64_t row_offset, void* stream);
 int rvlp_peer_barrier(int device, void* const* flag_blocks, int32_t n_ranks, int32_t my_rank, uint64_t epoch,
-                      void* stream);
+                      int64_t timeout_ms, void* stream);
 /* Device memory that other processes on this box can map: cudaMalloc + a 64-byte CUDA IPC handle (zero-filled);
  * rvlp_peer_open maps another process's block into this one.  Close what was opened, free what was allocated. */
 int rvlp_peer_alloc(int device, int64_t bytes, void** dev_ptr, void* handle64);

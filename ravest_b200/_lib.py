@@ -84,7 +84,7 @@ def load() -> C.CDLL:
     lib.rvlp_logprob_batch.argtypes = [vp, vp, i64, vp, vp]
     lib.rvlp_logprob_batch_host.argtypes = [vp, vp, i64, vp]
     lib.rvlp_logprob_batch_peers.argtypes = [vp, vp, i64, vp, i32, i64, vp]
-    lib.rvlp_peer_barrier.argtypes = [C.c_int, vp, i32, i32, C.c_uint64, vp]
+    lib.rvlp_peer_barrier.argtypes = [C.c_int, vp, i32, i32, C.c_uint64, i64, vp]
     lib.rvlp_peer_alloc.argtypes = [C.c_int, i64, C.POINTER(vp), vp]
     lib.rvlp_peer_open.argtypes = [C.c_int, vp, C.POINTER(vp)]
     lib.rvlp_peer_close.argtypes = [C.c_int, vp]

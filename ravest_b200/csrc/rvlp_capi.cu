@@ -619,14 +619,15 @@ int rvlp_logprob_batch_peers(rvlp_ctx* c, const double* theta_dev, int64_t S, do
 }
 
 int rvlp_peer_barrier(int device, void* const* flag_blocks, int32_t n_ranks, int32_t my_rank, uint64_t epoch,
-                      void* stream) {
-  if (!flag_blocks || n_ranks < 1 || n_ranks > kMaxPeers || my_rank < 0 || my_rank >= n_ranks)
+                      int64_t timeout_ms, void* stream) {
+  if (!flag_blocks || n_ranks < 1 || n_ranks > kMaxPeers || my_rank < 0 || my_rank >= n_ranks || timeout_ms < 1)
     return fail(RVLP_EINVAL, "bad arguments");
   DeviceGuard guard(device);
   PeerOut fl{};
   fl.n = n_ranks;
   for (int i = 0; i < n_ranks; ++i) fl.p[i] = reinterpret_cast<double*>(flag_blocks[i]);
-  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(fl, my_rank, (unsigned long long)epoch);
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(fl, my_rank, (unsigned long long)epoch,
+                                                          (unsigned long long)timeout_ms * 1000000ull);
   ++g_launches;
   CUDA_TRY(cudaGetLastError());
   return RVLP_OK;

@@ -67,9 +67,9 @@ struct DevProblem {
   const double* epochs;   // [t | vel | err2] x n_pad doubles, then n_pad int32 instrument ids
 };
 
-// Fused all-gather (multi-GPU): K1 stores a sample's log-probability straight into the gathered [S]
-// vector of EVERY rank - p[i] is rank i's buffer, mapped into this process by CUDA IPC, NVLink peer stores of
-// 8 bytes per sample - at row off + s, instead of a local vector that a collective copies afterwards.
+// Fused all-gather (multi-GPU): K1 stores a batch's log-probabilities straight into the gathered [S]
+// vector of EVERY rank - p[i] is rank i's buffer, mapped into this process by CUDA IPC; one coalesced NVLink peer
+// store per rank and batch - at rows off + s, instead of a local vector that a collective copies afterwards.
 constexpr int kMaxPeers = 8;
 struct PeerOut {
   int n;                  // 0: not in use
@@ -626,7 +626,7 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
         }
         ll = -0.5 * chi_finish(acc);
       }
-      if (lane == 0 || lane < peers.n) {                    // every lane holds ll (xor-butterfly) and reads lp
+      if (lane == 0) {
         double r;
         if (flags & (F_JIT | F_PRIOR | F_HYPER)) {
           r = -INFINITY;                                     // fit.py:3468, 3480-3482
@@ -635,15 +635,22 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
           r += P.jacobian;
           r += P.renorm;
         }
-        if (lane < peers.n) peers.p[lane][peers.off + s] = r;   // lane i -> rank i's gathered vector (peer store)
-        if (lane == 0) {
-          if (out) out[s] = r;
-          if (ll_out) ll_out[s] = ll;
-          if (lp_out) lp_out[s] = lp;
-        }
+        if (out) out[s] = r;
+        if (ll_out) ll_out[s] = ll;
+        if (lp_out) lp_out[s] = lp;
+        if (peers.n) scratch[g * rec] = r;                   // the record's lp slot is free now: park the result
       }
     }
     __syncwarp();
+    if (peers.n) {
+      // the batch's results - consecutive rows of the gathered vector - go to every rank as ONE coalesced store per
+      // rank (lane g = sample g): a sixth of the NVLink transactions of per-sample stores at config 3
+      const bool live = lane < n_cur && s_cur + lane < S;
+      const double r = live ? scratch[lane * rec] : 0.0;
+      for (int i = 0; i < peers.n; ++i)
+        if (live) peers.p[i][peers.off + s_cur + lane] = r;
+      __syncwarp();
+    }
   }
 }
 
@@ -865,21 +872,23 @@ __global__ void prior_kernel(rvlp_prior pr, const double* __restrict__ x, int64_
 // Cross-rank barrier after a launch with PeerOut (one warp; thread i talks to rank i).  The launch before it on the
 // stream has completed, so its peer stores are performed; thread i then publishes `epoch` in rank i's flag word for
 // this rank (release, system scope) and waits until rank i's epoch has arrived in this rank's own flag block
-// (acquire).  Kernels queued after it on the stream may read the gathered vector.  The wait is bounded (~2 s):
-// a rank that never arrives sets flags_self[kMaxPeers] = 1 instead of hanging the GPU.
-__global__ void peer_barrier_kernel(PeerOut flags, int my_rank, unsigned long long epoch) {
+// (acquire).  Kernels queued after it on the stream may read the gathered vector.  The wait is bounded by
+// timeout_ns of the global timer: a rank that never arrives sets flags_self[kMaxPeers] = 1 instead of hanging the GPU.
+__global__ void peer_barrier_kernel(PeerOut flags, int my_rank, unsigned long long epoch, unsigned long long timeout_ns) {
   const int i = threadIdx.x;
   if (i >= flags.n) return;
   unsigned long long* theirs = reinterpret_cast<unsigned long long*>(flags.p[i]) + my_rank;
   volatile unsigned long long* mine = reinterpret_cast<unsigned long long*>(flags.p[my_rank]) + i;
   __threadfence_system();
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
-  const long long t0 = clock64();
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (;;) {
-    unsigned long long v;
+    unsigned long long v, t;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
     if (v >= epoch) break;
-    if (clock64() - t0 > 4000000000ll) {
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > timeout_ns) {
       reinterpret_cast<unsigned long long*>(flags.p[my_rank])[kMaxPeers] = 1ull;
       break;
     }

@@ -31,7 +31,7 @@ def test_peer_store_epilogue_and_barrier_on_one_gpu(cuda):
     flags = cuda.zeros(128, dtype=cuda.int64, device="cuda")
     fl = (C.c_void_p * 1)(flags.data_ptr())
     for epoch in (1, 2, 3):
-        _lib.check(lib.rvlp_peer_barrier(0, fl, 1, 0, epoch, _lib.stream_ptr(0)))
+        _lib.check(lib.rvlp_peer_barrier(0, fl, 1, 0, epoch, 1000, _lib.stream_ptr(0)))
     cuda.cuda.synchronize()
     assert flags[0].item() == 3 and flags[8].item() == 0             # arrived at epoch 3, no timeout
     for b in bufs:
@@ -39,7 +39,7 @@ def test_peer_store_epilogue_and_barrier_on_one_gpu(cuda):
         assert bool((b[:lo] == 777.0).all()) and bool((b[lo + len(theta):] == 777.0).all())
     # a rank that never arrives: the wait gives up and says so instead of hanging the GPU
     two = (C.c_void_p * 2)(flags.data_ptr(), flags.data_ptr() + 512)
-    _lib.check(lib.rvlp_peer_barrier(0, two, 2, 0, 9, _lib.stream_ptr(0)))
+    _lib.check(lib.rvlp_peer_barrier(0, two, 2, 0, 9, 300, _lib.stream_ptr(0)))
     cuda.cuda.synchronize()
     assert flags[8].item() == 1
 
@@ -60,12 +60,12 @@ th = torch.as_tensor(theta[lo:hi], device="cuda")
 ref = post.ctx.logprob(torch.as_tensor(theta, device="cuda"))
 outs = []
 for it in range(4):                                                 # both halves of the double buffer, twice
-    g = rdist.sharded_logprob(lambda t: post.ctx.logprob(t), th, n_samples=S, theta_is_local=True, ctx=post.ctx)
+    g = rdist.sharded_logprob(lambda t: post.ctx.logprob(t), th, n_samples=S, theta_is_local=True, ctx=post.ctx, fused=True)
     outs.append(bool(torch.equal(g.view(torch.int64), ref.view(torch.int64))))
 pgs = list(post.ctx._peer_gathers.values())
 fused = bool(pgs) and pgs[0] is not None
 timed_out = pgs[0].timed_out() if fused else False
-n = rdist.sharded_logprob(lambda t: post.ctx.logprob(t), th, n_samples=S, theta_is_local=True)   # NCCL all-gather
+n = rdist.sharded_logprob(lambda t: post.ctx.logprob(t), th, n_samples=S, theta_is_local=True, fused=False)   # NCCL
 ok_nccl = bool(torch.equal(n.view(torch.int64), ref.view(torch.int64)))
 res = [None] * world
 dist.all_gather_object(res, (outs, fused, timed_out, ok_nccl))
