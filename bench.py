@@ -359,9 +359,8 @@ def sample_matrix_rows(torch, fit, barrier) -> dict:
     res["f1_rv_matrix"] = {"shape": f"c2 posterior: {S} samples x {T} times x 2 planets", "ms": ms,
                            "evals_per_s": S * T * 2 / ms * 1e3, "write_gbs": S * T * 8 / ms / 1e6}
     out = torch.empty((3, T), dtype=torch.float64, device="cuda")
-    n0 = _lib.launch_count()
     ms = time_kernel(torch, lambda: _lib.percentile_columns(m, [15.85, 50, 84.15], out=out), 5, 2, barrier) / 5
-    launches = (_lib.launch_count() - n0) // 7
+    launches = time_kernel.launches // 5
     res["f2_percentile_bands"] = {"shape": f"{S} x {T} fp64 matrix ({S * T * 8 / 1e6:.0f} MB), q = [15.85, 50, 84.15]",
                                   "ms": ms, "launches_per_call": launches,
                                   "algorithmic_gbs": S * T * 8 / ms / 1e6,

@@ -124,13 +124,18 @@ struct K1Shape {
   int smem;         // dynamic shared memory
   int max_nb;       // samples per prologue batch
 };
-static K1Shape k1_shape(int v, const DevProblem& P, const SmemLayout& L) {
+static K1Shape k1_shape(int v, const DevProblem& P, const SmemLayout& L, bool peers = false) {
   const bool ge = P.epochs_global != 0;
   K1Shape s{};
   s.threads = kThreads;
   s.workers = kWarps;
   s.smem = L.total;
   s.max_nb = P.batch_cap > kG ? P.batch_cap : kG;
+  if (peers) {   // the instantiation with the fused all-gather epilogue (rvlp_logprob_batch_peers)
+    if (v == 1) s.fn = ge ? logprob_kernel<2, 3, true, true> : logprob_kernel<2, 3, false, true>;
+    else s.fn = ge ? logprob_kernel<kW, RVLP_MIN_BLOCKS, true, true> : logprob_kernel<kW, RVLP_MIN_BLOCKS, false, true>;
+    return s;
+  }
   if (v == 1) s.fn = ge ? logprob_kernel<2, 3, true> : logprob_kernel<2, 3, false>;
   else s.fn = ge ? logprob_kernel<kW, RVLP_MIN_BLOCKS, true> : logprob_kernel<kW, RVLP_MIN_BLOCKS, false>;
   return s;
@@ -472,8 +477,10 @@ int rvlp_ctx_create(const rvlp_desc* d, const double* time, const double* vel, c
     rvlp_ctx_destroy(c);
     return rc;
   }
-  for (int v = 0; v < kK1Variants; ++v)
+  for (int v = 0; v < kK1Variants; ++v) {
     CTX_TRY(cudaFuncSetAttribute(k1_shape(v, P, L).fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+    CTX_TRY(cudaFuncSetAttribute(k1_shape(v, P, L, true).fn, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
+  }
   CTX_TRY(cudaFuncSetAttribute(rv_matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   CTX_TRY(cudaFuncSetAttribute(walker_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->max_smem));
   if (P.n_hyper) {
@@ -528,8 +535,8 @@ static int launch_logprob(rvlp_ctx* c, const double* theta, int64_t S, double* o
   if (peer_out) peers = *peer_out;
   int grid = 0;
   SmemLayout L = smem_layout(c->P);
-  K1Shape shape = k1_shape(c->k1, c->P, L);
-  if (shape.smem > c->max_smem) shape = k1_shape(0, c->P, L);   // rings do not fit next to this many epochs
+  K1Shape shape = k1_shape(c->k1, c->P, L, peers.n > 0);
+  if (shape.smem > c->max_smem) shape = k1_shape(0, c->P, L, peers.n > 0);   // rings do not fit next to this many epochs
   const k1_fn kern = shape.fn;
   const int smem = shape.smem;
   int rc = grid_for(c->device, (const void*)kern, smem, INT_MAX, &grid, shape.threads);   // full wave

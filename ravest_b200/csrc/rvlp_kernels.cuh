@@ -525,7 +525,7 @@ __device__ __forceinline__ void sample_chi_pipelined(const DevProblem& P, const 
 // is 10 % ahead on the high-eccentricity config and 4 % on 120-epoch data); rvlp_ctx_autotune times both on
 // the caller's own rows.  A lane visits its epochs (lane, lane + 32, ...) in ascending order for either W, so
 // the choice never changes a bit of the result.
-template <int W, int MB, bool GE>
+template <int W, int MB, bool GE, bool PEERS = false>
 __global__ void __launch_bounds__(kThreads, MB)
 logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double* __restrict__ out,
                double* __restrict__ ll_out, double* __restrict__ lp_out, int nb,
@@ -638,11 +638,11 @@ logprob_kernel(DevProblem P, const double* __restrict__ theta, int64_t S, double
         if (out) out[s] = r;
         if (ll_out) ll_out[s] = ll;
         if (lp_out) lp_out[s] = lp;
-        if (peers.n) scratch[g * rec] = r;                   // the record's lp slot is free now: park the result
+        if (PEERS) scratch[g * rec] = r;                     // the record's lp slot is free now: park the result
       }
     }
     __syncwarp();
-    if (peers.n) {
+    if (PEERS) {   // (a separate instantiation: the single-GPU kernel carries none of this)
       // the batch's results - consecutive rows of the gathered vector - go to every rank as ONE coalesced store per
       // rank (lane g = sample g): a sixth of the NVLink transactions of per-sample stores at config 3
       const bool live = lane < n_cur && s_cur + lane < S;
