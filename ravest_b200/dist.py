@@ -175,7 +175,8 @@ def sharded_logprob(eval_fn: Callable, theta, n_samples: int | None = None, grou
         fused = os.environ.get("RVLP_PEER_GATHER", "1") != "0"
     if (fused and ctx is not None and world > 1 and world <= 8 and getattr(theta, "is_cuda", False)
             and not ctx.desc.is_gp and dist.get_backend(group) == "nccl"):
-        pg = _peer_gather_for(ctx, S, theta.device.index, group)
+        dev = theta.device.index if theta.device.index is not None else torch.cuda.current_device()
+        pg = _peer_gather_for(ctx, S, dev, group)
         if pg is not None:
             out = pg.logprob(ctx, local, lo)
             return out.clone() if copy else out
