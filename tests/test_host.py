@@ -180,6 +180,9 @@ def _gloo_worker(rank, world, port, q):
     full = dist.sharded_logprob(eval_fn, th)
     lo, hi = dist.shard_bounds(len(theta), world, rank)
     local = dist.sharded_logprob(eval_fn, th[lo:hi], n_samples=len(theta), theta_is_local=True)
+    # a `ctx` on CPU tensors / gloo must not take the fused (CUDA IPC + NCCL only) path, whatever the default says
+    again = dist.sharded_logprob(eval_fn, th, ctx=object(), fused=True)
+    assert torch.equal(again, full) or bool(torch.isnan(full).any())
     q.put((rank, full.numpy(), local.numpy()))
     td.destroy_process_group()
 
