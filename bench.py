@@ -4,9 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3] [--scaling strong|weak]
 
 A "step" is one pass of the hot path over one batch: S samples x N epochs x n_pl planets through
-LogPosterior.log_probability_batch (one kernel launch per rank, plus one all-gather of the S log-probs when N > 1).
+LogPosterior.log_probability_batch (one kernel launch per rank; when N > 1 the all-gather of the S log-probs is fused
+into that kernel as NVLink peer stores + a one-warp flag barrier, and the NCCL all-gather is timed beside it).
 Headline workload: BASELINE config 3 as named - 5 planets, 1000 epochs, **1e6 samples in total, sharded over the N
-GPUs** (`"scaling": "strong"`, the product's `ravest_b200.dist.sharded_logprob` on NCCL).  The weak-scaling point
+GPUs** (`"scaling": "strong"`, the product's `ravest_b200.dist.sharded_logprob`).  The weak-scaling point
 (1e6 samples PER GPU) is measured in the same run and reported under `weak_scaling`.  Prints ONE JSON line.
 
   value      (sample x epoch x planet) evaluations/s, whole job, theta resident in HBM
@@ -625,7 +626,8 @@ def main() -> None:
                 roofline["achieved"] = alg
                 roofline["frac"] = alg / (peak_flops / 1e12)
                 roofline["note"] += "  (no committed ncu capture found: frac falls back to the algorithmic figure)"
-        par = (f"{m['total']} samples sharded x{world} (ravest_b200.dist.sharded_logprob), 1 all-gather of log-probs per step"
+        par = (f"{m['total']} samples sharded x{world} (ravest_b200.dist.sharded_logprob), the all-gather of log-probs fused "
+               f"into the kernel (see `gather`)"
                if args.scaling == "strong" else f"{S} samples per GPU x{world}, 1 all-gather of log-probs per step")
         line = {
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world,
